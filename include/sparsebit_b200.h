@@ -1,0 +1,229 @@
+/*
+ * sparsebit_b200.h -- C-ABI of the B200-native (sm_100a) fake-quantization / observer / sparser /
+ * GPTQ-int4 hot path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * megvii-research/Sparsebit tree, commit f473aef).  The reference exposes this path as two pybind
+ * modules (`fake_quant`, `cuda_kernel`) plus chains of ATen ops inside its Python observers and
+ * sparsers; INTEGRATION.md shows the ctypes / pybind stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - All `const float*` / `float*` data arguments are DEVICE pointers (fp32, contiguous) unless the
+ *     function name ends in `_host`, in which case the data arguments are HOST pointers (ideally
+ *     pinned) and the call performs the H2D / D2H copies itself, pipelined over internal streams.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Device
+ *     entry points are asynchronous on that stream, never synchronise the host, keep no global
+ *     state and are re-entrant (the reference kernels have the same contract:
+ *     sparsebit/quantization/torch_extensions/fake_quant_tensor.cu:83,152,212,297).
+ *   - Return value: 0 on success, a negative SB200_E_* code on error; `sb200_last_error()` returns
+ *     a thread-local human readable message.  The reference reports the same conditions as
+ *     C++ exceptions -> Python RuntimeError (torch_extensions/common.cuh:27-55,
+ *     large_language_models/llama/quantization/cuda/cuda_kernel_4bit.cu:44-60); the Python host
+ *     layer (`sparsebit_b200/`) turns non-zero codes back into RuntimeError.
+ *   - `rounding`: 0 = half-to-even (the only value the reference ever passes,
+ *     quantizers/quant_tensor.py:99,109,147,151), 1 = half-up, 2 = half-down
+ *     (torch_extensions/common.cuh:21-23).
+ *   - Numerics follow the reference's *CPU Python* path (quant_tensor.py:181-184), which is the
+ *     parity oracle: zp = rint(zero_point) half-to-even, IEEE division x/scale, float clamp,
+ *     (q - zp) * scale without FMA contraction.  Finite inputs agree bit-for-bit with both the
+ *     reference CPU path and its CUDA kernels; NaN propagates like torch.clamp.
+ */
+#ifndef SPARSEBIT_B200_H_
+#define SPARSEBIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define SB200_OK 0
+#define SB200_E_INVALID (-1)   /* bad argument (null pointer, empty tensor, bad size) */
+#define SB200_E_CUDA (-2)      /* a CUDA runtime call failed */
+#define SB200_E_UNSUPPORTED (-3)
+#define SB200_E_WORKSPACE (-4) /* caller workspace too small */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* sb200_last_error(void);
+int sb200_version(void);
+/* Number of SMs of the current device (grid sizing is derived from it). */
+int sb200_sm_count(void);
+/* Select an implementation variant for the streaming QDQ kernels: 0 = auto, 1 = 128-bit LDG/STG
+ * register pipeline, 2 = TMA (cp.async.bulk) shared-memory ring.  For benchmarking only. */
+int sb200_set_variant(int variant);
+
+/* ---- (1) Quantizer.forward: quantize -> dequantize ---------------------------------------
+ * Replaces fake_quant.quant_pertensor_forward   (torch_extensions/export.cc:4,
+ *          fake_quant_tensor.cu:50-94)   and the CPU branch quant_tensor.py:181-184.
+ * out[i] = (clamp(round(x[i]/scale[0]) + rint(zp[0]), qmin, qmax) - rint(zp[0])) * scale[0]
+ * scale / zero_point: device pointers to 1 float each. */
+int sb200_qdq_pertensor_fwd(const float* x, const float* scale, const float* zero_point,
+                            float* out, int64_t n, int qmin, int qmax, int rounding, void* stream);
+
+/* Replaces fake_quant.quant_perchannel_forward (export.cc:6, fake_quant_tensor.cu:170-224).
+ * x is viewed as [outer, C, inner] (inner = prod(sizes[ch_axis+1:]), fake_quant_tensor.cu:203-208);
+ * scale / zero_point hold C floats and are indexed by c = (i / inner) % C. */
+int sb200_qdq_perchannel_fwd(const float* x, const float* scale, const float* zero_point,
+                             float* out, int64_t outer, int64_t channels, int64_t inner, int qmin,
+                             int qmax, int rounding, void* stream);
+
+/* Fused QDQ + MinMax observer statistics of the INPUT x (new; the reference runs
+ * Quantizer.forward and observers/minmax.py:14-25 as separate ATen passes).  `minmax_state` is a
+ * running state of 2 uint32 {enc(min), enc(max)} created by sb200_minmax_init(.., 1, ..) and
+ * decoded by sb200_minmax_read.  8 B/elem of HBM traffic, the kernel the 70 % roofline target is
+ * quoted on. */
+int sb200_qdq_stats_pertensor_fwd(const float* x, const float* scale, const float* zero_point,
+                                  float* out, uint32_t* minmax_state, int64_t n, int qmin, int qmax,
+                                  int rounding, void* stream);
+
+/* Host-buffer (end-to-end) variants: x_host/out_host are host pointers; scale/zero_point are HOST
+ * floats.  Copies are chunked and overlapped with the kernel on internal streams; the call
+ * returns after the last D2H copy completed.  minmax_host receives {min, max} (may be NULL). */
+int sb200_qdq_pertensor_fwd_host(const float* x_host, float scale, float zero_point,
+                                 float* out_host, float* minmax_host, int64_t n, int qmin, int qmax,
+                                 int rounding);
+int sb200_qdq_perchannel_fwd_host(const float* x_host, const float* scale_host,
+                                  const float* zero_point_host, float* out_host, int64_t outer,
+                                  int64_t channels, int64_t inner, int qmin, int qmax,
+                                  int rounding);
+
+/* ---- STE backward ------------------------------------------------------------------------
+ * Replaces fake_quant.quant_pertensor_backward (export.cc:5, fake_quant_tensor.cu:97-167) and
+ * quant_perchannel_backward (export.cc:7, fake_quant_tensor.cu:227-314).
+ *   vq = round(x/s) + zp ;  gx = gy * [qmin <= vq <= qmax]
+ *   gs  = sum gy * { round(x/s) - x/s  inside ; (qmin - zp) below ; (qmax - zp) above }
+ *   gzp = sum -s * gy * [vq outside [qmin, qmax]]         (per-tensor semantics for both, Q4)
+ * gs / gzp may be NULL (the reference's enable_gs / enable_gzp = requires_grad flags).  They are
+ * produced by a deterministic two-stage reduction (fp32 per thread, fp64 across CTAs) instead of
+ * float atomics.  `workspace` must hold sb200_qdq_bwd_workspace_bytes(...) bytes. */
+size_t sb200_qdq_bwd_workspace_bytes(int64_t outer, int64_t channels, int64_t inner);
+int sb200_qdq_pertensor_bwd(const float* x, const float* scale, const float* zero_point,
+                            const float* grad_y, float* grad_x, float* grad_scale, float* grad_zp,
+                            int64_t n, int qmin, int qmax, int rounding, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int sb200_qdq_perchannel_bwd(const float* x, const float* scale, const float* zero_point,
+                             const float* grad_y, float* grad_x, float* grad_scale, float* grad_zp,
+                             int64_t outer, int64_t channels, int64_t inner, int qmin, int qmax,
+                             int rounding, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (2) Observer calibration reductions -------------------------------------------------
+ * MinMax (observers/minmax.py:14-25 -- torch.cat + min/max).  Streaming: the state is updated
+ * in place per batch, nothing is cached or concatenated.  State layout: uint32[2*C], entry 2c =
+ * order-preserving encoding of the running min of channel c, 2c+1 = of the running max; a third
+ * implicit NaN flag is encoded as enc(NaN).  C = 1 for per-tensor. */
+int sb200_minmax_init(uint32_t* state, int64_t channels, void* stream);
+int sb200_observe_minmax(const float* x, int64_t n, uint32_t* state, void* stream);
+int sb200_observe_minmax_perchannel(const float* x, int64_t outer, int64_t channels, int64_t inner,
+                                    uint32_t* state, void* stream);
+/* Decode to floats: out_min[C], out_max[C] (device pointers). */
+int sb200_minmax_read(const uint32_t* state, int64_t channels, float* out_min, float* out_max,
+                      void* stream);
+
+/* KL-histogram (observers/kl_histogram.py:47-50 -> torch.histc on CPU).  counts[bins] (int64) is
+ * accumulated in place.  `range` = device {lo, hi}.  Bin rule = ATen's CPU histc
+ * (HistogramKernel.cpp, linear interpolation): pos = (int64)(((x - lo) * bins) / (hi - lo)) in
+ * fp32 with IEEE division, pos == bins folded into the last bin, x outside [lo, hi] and NaN
+ * ignored. */
+int sb200_observe_hist(const float* x, int64_t n, const float* range, int bins, int64_t* counts,
+                       void* stream);
+
+/* MSE observer sweep (observers/mse.py:46-61): for each row r (R rows of `row_len` contiguous
+ * floats; R = 1 for per-tensor) and each of `ncand` candidate (scale, zp) pairs
+ * cand_scale/cand_zp[r*ncand + i], accumulate sse[r*ncand + i] += sum_j (x - qdq_i(x))^2 in one
+ * pass over x (the reference does ncand=80 full QDQ + loss passes).  sse is fp64, accumulated in
+ * place (so several cached batches / several GPUs add up); workspace from
+ * sb200_mse_workspace_bytes. */
+size_t sb200_mse_workspace_bytes(int64_t rows, int64_t row_len, int ncand);
+int sb200_observe_mse_sweep(const float* x, int64_t rows, int64_t row_len, const float* cand_scale,
+                            const float* cand_zp, int ncand, int qmin, int qmax, double* sse,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact order statistics by MSB-first radix select on an order-preserving 32-bit key
+ * (replaces torch.kthvalue in observers/percentile.py:34-43 and torch.sort in
+ * sparse/sparsers/l1norm.py:18-22).  Three passes over the data (11 + 11 + 10 key bits); each pass
+ * is   sb200_select_hist (adds this shard's digit histogram for every live target)
+ *      [optional: SUM all-reduce of `hist` across GPUs]
+ *      sb200_select_scan (finds each target's bucket, narrows prefix and rank, clears hist).
+ * `sel` is an opaque device state of SB200_SELECT_STATE_WORDS uint64 per target; `hist` holds
+ * ntargets * 2048 int64.  key_mode 0: key = enc(x) (signed order); 1: key = enc(|x|).
+ * Row-batched: `rows` independent rows of `row_len` floats, targets are per row
+ * (ntargets_per_row of them), state index = row * ntargets_per_row + t. */
+#define SB200_SELECT_STATE_WORDS 4
+#define SB200_SELECT_BINS 2048
+/* Reset `sel` (ntargets_total states) and `hist`; ranks (device, 0-based, may be NULL = 0). */
+int sb200_select_init(uint64_t* sel, int64_t* hist, int64_t ntargets_total, const int64_t* ranks,
+                      void* stream);
+int sb200_select_hist(const float* x, int64_t rows, int64_t row_len, int ntargets_per_row,
+                      const uint64_t* sel, int64_t* hist, int pass, int key_mode, void* stream);
+/* Same, and in pass 0 also accumulates sign_counts[row*2+0] += #(x < 0),
+ * sign_counts[row*2+1] += #(x >= 0) from the same read of x (percentile.py:27-28). */
+int sb200_select_hist_counts(const float* x, int64_t rows, int64_t row_len, int ntargets_per_row,
+                             const uint64_t* sel, int64_t* hist, int pass, int key_mode,
+                             int64_t* sign_counts, void* stream);
+int sb200_select_scan(uint64_t* sel, int64_t* hist, int64_t rows, int ntargets_per_row, int pass,
+                      void* stream);
+/* values[t] = float whose key is the selected one (valid after the pass-2 scan). */
+int sb200_select_read(const uint64_t* sel, int64_t ntargets_total, int key_mode, float* values,
+                      void* stream);
+
+/* Percentile observer helpers (observers/percentile.py:27-43).
+ * counts[row*2 + 0] += #(x < 0), counts[row*2 + 1] += #(x >= 0)  (int64, in place). */
+int sb200_count_sign(const float* x, int64_t rows, int64_t row_len, int64_t* counts, void* stream);
+/* Writes the two ranks of every row straight into its select states (2 targets per row):
+ *   target 0 (min side): 0-based rank max(round(neg*alpha), 1) - 1
+ *   target 1 (max side): 0-based rank total - max(round(pos*alpha), 0) - 1
+ * with Python round() (half-to-even on the double product) -- percentile.py:36-42.
+ * total[row] = number of elements of the row (NaN included), device int64. */
+int sb200_percentile_ranks(const int64_t* counts, const int64_t* total, int64_t rows, double alpha,
+                           uint64_t* sel, void* stream);
+
+/* ---- (3) Sparser -------------------------------------------------------------------------
+ * mask[i] = |w[i]| > thresh[0]   (sparse/sparsers/l1norm.py:23; strict, ties pruned; uint8 0/1 =
+ * torch.bool storage).  thresh is a device float (from the radix select above with key_mode 1
+ * and rank min(int(n*ratio), n-1), l1norm.py:19-21). */
+int sb200_mask_gt(const float* w, const float* thresh, uint8_t* mask, int64_t n, void* stream);
+/* out = w * mask    (sparse/modules/conv.py:40, linear.py:31).  mask: uint8 (bool). */
+int sb200_mask_apply(const float* w, const uint8_t* mask, float* out, int64_t n, void* stream);
+/* out = w * mask_f32   (mask stored as float ones_like when ratio == 0, l1norm.py:15-16). */
+int sb200_mask_apply_f32(const float* w, const float* mask, float* out, int64_t n, void* stream);
+/* Fused  out = QDQ_perchannel(w * mask)  (mask-apply feeding the weight quantizer, one pass,
+ * 9 B/elem instead of 4+1+4 + 4+4). */
+int sb200_mask_apply_qdq_perchannel(const float* w, const uint8_t* mask, const float* scale,
+                                    const float* zero_point, float* out, int64_t outer,
+                                    int64_t channels, int64_t inner, int qmin, int qmax,
+                                    int rounding, void* stream);
+
+/* ---- (4) GPTQ int4 group-wise dequant-matmul --------------------------------------------
+ * Replaces cuda_kernel.vecquant4matmul / vecgroupquant4matmul
+ * (large_language_models/llama/quantization/cuda/cuda_kernel.cpp:10-23,70,73;
+ *  cuda_kernel_4bit.cu:36-180):
+ *   out[m, n] += sum_k (scales[n*G + k/gs] * nib(qweight[k/8, n], k%8) - zeros[n*G + k/gs]) * x[m, k]
+ * x: [M, K] fp32; qweight: int32 [ceil(K/8), N], 8 nibbles per word along K, LSB = lowest k
+ * (utils/quant.py:220-225); out: [M, N] fp32, PRE-INITIALISED (bias) and accumulated in place;
+ * scales / zeros (= zero*scale, utils/quant.py:188): fp32 [N, G], G = ceil(K / group_size).
+ * group_size == 0 means one group (= K), like vecquant4matmul; otherwise it must be a multiple of
+ * 128 (cuda_kernel_4bit.cu:60).  Large-M problems with TMA-compatible shapes run on tcgen05
+ * tensor cores (split-fp16 activations, exact int4 operands, fp32 TMEM accumulation, per-group
+ * scale/zero applied in the epilogue); everything else runs the HBM-bound SIMT path.
+ * `workspace` from sb200_gptq4_workspace_bytes (may be 0 bytes / NULL for the SIMT path). */
+size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size);
+int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales,
+                       const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
+                       int group_size, void* workspace, size_t workspace_bytes, void* stream);
+/* Force a GPTQ implementation: 0 = auto, 1 = SIMT, 2 = tcgen05.  For tests / benchmarking. */
+int sb200_gptq4_set_impl(int impl);
+
+/* Number of kernels this library launched since load (bench.py's `gpu_launches`). */
+int64_t sb200_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSEBIT_B200_H_ */

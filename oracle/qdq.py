@@ -1,0 +1,91 @@
+"""Oracle: quantize -> dequantize and its STE backward (numpy, IEEE fp32 op by op).
+
+numpy float32 ufuncs (divide, rint, add, clip-by-comparison, subtract, multiply) are correctly
+rounded IEEE operations, i.e. bit-identical to the ATen CPU ops the reference chains.
+"""
+import numpy as np
+
+F32 = np.float32
+
+
+def _round(v, rounding=0):
+    """rounding 0: half-to-even (torch.round); 1: floor(v + .5); 2: ceil(v - .5)
+    (sparsebit/quantization/torch_extensions/common.cuh:62-76)."""
+    if rounding == 0:
+        return np.rint(v)
+    if rounding == 1:
+        return np.floor(v + F32(0.5))
+    if rounding == 2:
+        return np.ceil(v - F32(0.5))
+    raise ValueError(rounding)
+
+
+def _clamp_keep_nan(v, lo, hi):
+    """torch.clamp semantics: NaN stays NaN."""
+    v = np.where(v < F32(lo), F32(lo), v)
+    v = np.where(v > F32(hi), F32(hi), v)
+    return v.astype(F32)
+
+
+def _bcast(param, x, ch_axis):
+    param = np.asarray(param, dtype=F32).reshape(-1)
+    if param.size == 1:
+        return param.reshape([1] * x.ndim)
+    shape = [1] * x.ndim
+    shape[ch_axis] = -1
+    return param.reshape(shape)
+
+
+def qdq(x, scale, zero_point, qmin, qmax, ch_axis=0, rounding=0):
+    """ort_fake_quant CPU branch, sparsebit/quantization/quantizers/quant_tensor.py:181-184:
+        zp = zero_point.round(); x_q = clamp((x / scale).round() + zp, qmin, qmax)
+        x_dq = (x_q - zp) * scale
+    ``scale`` / ``zero_point`` hold 1 value (per-tensor) or C values along ``ch_axis``
+    (per-channel, fake_quant_tensor.cu:183 ``c = (i / inner) % C``)."""
+    x = np.asarray(x, dtype=F32)
+    s = _bcast(scale, x, ch_axis)
+    zp = np.rint(_bcast(zero_point, x, ch_axis))
+    with np.errstate(all="ignore"):
+        q = _round((x / s).astype(F32), rounding)
+        xq = _clamp_keep_nan((q + zp).astype(F32), qmin, qmax)
+        return ((xq - zp).astype(F32) * s).astype(F32)
+
+
+def quantize_int(x, scale, zero_point, qmin, qmax, ch_axis=0, rounding=0):
+    """The integer grid point x_q (the 'integer clamp path' that must be bit-exact)."""
+    x = np.asarray(x, dtype=F32)
+    s = _bcast(scale, x, ch_axis)
+    zp = np.rint(_bcast(zero_point, x, ch_axis))
+    with np.errstate(all="ignore"):
+        q = _round((x / s).astype(F32), rounding)
+        return _clamp_keep_nan((q + zp).astype(F32), qmin, qmax)
+
+
+def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0):
+    """STE backward.  The reference has no CPU implementation (quant_tensor.py:113-116); restated
+    from MySTE.backward (quant_tensor.py:46-71) and the CUDA kernels
+    (torch_extensions/fake_quant_tensor.cu:111-131, 243-268), reductions in fp64:
+        vq  = round(x/s) + zp
+        gx  = gy * [qmin <= vq <= qmax]
+        gs  = sum gy * (round(x/s) - x/s | qmin - zp | qmax - zp)
+        gzp = sum -s * gy * [vq outside]            (per-tensor rule for both layouts, Q4)
+    Returns gx (fp32), gs, gzp (fp64, shape [C] or [1])."""
+    x = np.asarray(x, dtype=F32)
+    gy = np.asarray(grad_y, dtype=F32)
+    s = _bcast(scale, x, ch_axis)
+    zp = np.rint(_bcast(zero_point, x, ch_axis))
+    with np.errstate(all="ignore"):
+        q = (x / s).astype(F32)
+        r = _round(q, rounding)
+        vq = (r + zp).astype(F32)
+    below = vq < F32(qmin)
+    inside = (vq >= F32(qmin)) & (vq <= F32(qmax))
+    gx = np.where(inside, gy, F32(0)).astype(F32)
+    term = np.where(inside, (r - q).astype(F32), np.where(below, (F32(qmin) - zp).astype(F32), (F32(qmax) - zp).astype(F32)))
+    gs_e = term.astype(np.float64) * gy.astype(np.float64)
+    gz_e = np.where(inside, 0.0, (-s).astype(np.float64) * gy.astype(np.float64))
+    nch = np.asarray(scale).size
+    if nch == 1:
+        return gx, np.array([gs_e.sum()]), np.array([gz_e.sum()])
+    axes = tuple(a for a in range(x.ndim) if a != ch_axis)
+    return gx, gs_e.sum(axis=axes), gz_e.sum(axis=axes)

@@ -1,0 +1,314 @@
+// bwd.cu -- STE backward of the fake-quant op for sm_100a.
+//
+// Replaces (reference, megvii-research/Sparsebit):
+//   sparsebit/quantization/torch_extensions/fake_quant_tensor.cu:97-167   per-tensor backward
+//   sparsebit/quantization/torch_extensions/fake_quant_tensor.cu:227-314  per-channel backward
+//   formula restated from quantizers/quant_tensor.py:46-71 (MySTE.backward)
+//
+//   vq  = round(x/s) + zp
+//   gx  = gy            if qmin <= vq <= qmax else 0
+//   gs  = sum gy * (round(x/s) - x/s)   inside ;  gy * (qmin - zp) below ;  gy * (qmax - zp) above
+//   gzp = sum -s * gy                   outside the range, 0 inside
+//
+// 12 B/elem (x, gy in; gx out).  The reference reduces gs/gzp with a block reduce + float
+// atomicAdd *per grid-stride iteration* and has __syncthreads() under divergent control flow
+// (fake_quant_tensor.cu:123,128,260,265); here every tile produces one fp64 partial that a second
+// tiny kernel sums in a fixed order -> deterministic, no atomics.  The per-channel gzp mask uses the
+// per-tensor rule (vq <= qmax is inside); the reference's per-channel kernel uses vq < qmax
+// (fake_quant_tensor.cu:264), which SURVEY.md Q4 identifies as a bug.
+#include "common.cuh"
+
+namespace sb200 {
+
+constexpr int kThreads = 256;
+constexpr long long kTile = 8192;  // elements per reduction tile
+
+struct BwdAcc {
+  float gs, gzp;
+};
+
+template <int ROUNDING>
+__device__ __forceinline__ float bwd1(float x, float gy, const QP& p, float lo_term, float hi_term, BwdAcc& a,
+                                      int rounding) {
+  const float q = div_exact(x, p);
+  float r;
+  if (ROUNDING == 0) r = rintf(q);
+  else r = rounding == 1 ? floorf(__fadd_rn(q, 0.5f)) : (rounding == 2 ? ceilf(__fsub_rn(q, 0.5f)) : rintf(q));
+  const float vq = __fadd_rn(r, p.zp);
+  const bool below = vq < p.qmin;
+  const bool inside = (vq >= p.qmin) && (vq <= p.qmax);
+  const float term = inside ? __fsub_rn(r, q) : (below ? lo_term : hi_term);
+  a.gs = fmaf(term, gy, a.gs);
+  a.gzp += inside ? 0.f : __fmul_rn(-p.s, gy);
+  return inside ? gy : 0.f;
+}
+
+// Process `len` contiguous elements cooperatively (thread rank t of nthr).
+template <int ROUNDING>
+__device__ __forceinline__ void span_bwd(const float* __restrict__ x, const float* __restrict__ gy,
+                                         float* __restrict__ gx, long long len, int t, int nthr, const QP& p,
+                                         BwdAcc& a, int rounding) {
+  const float lo_term = __fsub_rn(p.qmin, p.zp), hi_term = __fsub_rn(p.qmax, p.zp);
+  const uintptr_t ax = reinterpret_cast<uintptr_t>(x) & 15u;
+  const bool vec = (ax == (reinterpret_cast<uintptr_t>(gy) & 15u)) && (ax == (reinterpret_cast<uintptr_t>(gx) & 15u));
+  if (!vec) {
+    for (long long i = t; i < len; i += nthr) gx[i] = bwd1<ROUNDING>(__ldcs(x + i), __ldcs(gy + i), p, lo_term, hi_term, a, rounding);
+    return;
+  }
+  long long head = ((16 - ax) & 15u) >> 2;
+  if (head > len) head = len;
+  for (long long i = t; i < head; i += nthr) gx[i] = bwd1<ROUNDING>(__ldcs(x + i), __ldcs(gy + i), p, lo_term, hi_term, a, rounding);
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const float4* g4 = reinterpret_cast<const float4*>(gy + head);
+  float4* o4 = reinterpret_cast<float4*>(gx + head);
+  const long long nv = (len - head) >> 2;
+  long long i = t;
+  for (; i + nthr < nv; i += 2LL * nthr) {
+    const float4 xa = ld_stream4(x4 + i), ga = ld_stream4(g4 + i);
+    const float4 xb = ld_stream4(x4 + i + nthr), gb = ld_stream4(g4 + i + nthr);
+    float4 r;
+    r.x = bwd1<ROUNDING>(xa.x, ga.x, p, lo_term, hi_term, a, rounding);
+    r.y = bwd1<ROUNDING>(xa.y, ga.y, p, lo_term, hi_term, a, rounding);
+    r.z = bwd1<ROUNDING>(xa.z, ga.z, p, lo_term, hi_term, a, rounding);
+    r.w = bwd1<ROUNDING>(xa.w, ga.w, p, lo_term, hi_term, a, rounding);
+    st_stream4(o4 + i, r);
+    r.x = bwd1<ROUNDING>(xb.x, gb.x, p, lo_term, hi_term, a, rounding);
+    r.y = bwd1<ROUNDING>(xb.y, gb.y, p, lo_term, hi_term, a, rounding);
+    r.z = bwd1<ROUNDING>(xb.z, gb.z, p, lo_term, hi_term, a, rounding);
+    r.w = bwd1<ROUNDING>(xb.w, gb.w, p, lo_term, hi_term, a, rounding);
+    st_stream4(o4 + i + nthr, r);
+  }
+  for (; i < nv; i += nthr) {
+    const float4 xa = ld_stream4(x4 + i), ga = ld_stream4(g4 + i);
+    float4 r;
+    r.x = bwd1<ROUNDING>(xa.x, ga.x, p, lo_term, hi_term, a, rounding);
+    r.y = bwd1<ROUNDING>(xa.y, ga.y, p, lo_term, hi_term, a, rounding);
+    r.z = bwd1<ROUNDING>(xa.z, ga.z, p, lo_term, hi_term, a, rounding);
+    r.w = bwd1<ROUNDING>(xa.w, ga.w, p, lo_term, hi_term, a, rounding);
+    st_stream4(o4 + i, r);
+  }
+  for (long long e = head + (nv << 2) + t; e < len; e += nthr)
+    gx[e] = bwd1<ROUNDING>(__ldcs(x + e), __ldcs(gy + e), p, lo_term, hi_term, a, rounding);
+}
+
+// Tiles: x viewed as rows of `inner` elements; tile = (row, j-th chunk of kTile).  A CTA (CTA_TILE) or
+// a warp handles one tile and writes partial[tile] = {gs, gzp} in fp64.
+template <bool CTA_TILE, int ROUNDING>
+__global__ void __launch_bounds__(kThreads) bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                            float* __restrict__ gx, const float* __restrict__ scale,
+                                                            const float* __restrict__ zero_point, long long rows,
+                                                            long long inner, int channels, float qmin, float qmax,
+                                                            int rounding, double2* __restrict__ partial) {
+  __shared__ double s_red[2][kThreads / 32];
+  const long long tpr = (inner + kTile - 1) / kTile;
+  const long long total = rows * tpr;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long first = CTA_TILE ? blockIdx.x : (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const long long stride = CTA_TILE ? gridDim.x : (((long long)gridDim.x * blockDim.x) >> 5);
+  for (long long tile = first; tile < total; tile += stride) {
+    const long long row = tile / tpr, j = tile - row * tpr;
+    const long long off = row * inner + j * kTile;
+    const long long len = (inner - j * kTile) < kTile ? (inner - j * kTile) : kTile;
+    const int c = (int)(row % channels);
+    QP p;
+    p.set(__ldg(scale + c), __ldg(zero_point + c));
+    p.qmin = qmin;
+    p.qmax = qmax;
+    BwdAcc a = {0.f, 0.f};
+    span_bwd<ROUNDING>(x + off, gy + off, gx + off, len, CTA_TILE ? threadIdx.x : lane, CTA_TILE ? blockDim.x : 32,
+                       p, a, rounding);
+    if (partial) {
+      const double gs = warp_sum((double)a.gs), gz = warp_sum((double)a.gzp);
+      if (CTA_TILE) {
+        if (lane == 0) {
+          s_red[0][wid] = gs;
+          s_red[1][wid] = gz;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) {
+            t0 += s_red[0][w];
+            t1 += s_red[1][w];
+          }
+          partial[tile] = make_double2(t0, t1);
+        }
+        __syncthreads();
+      } else if (lane == 0) {
+        partial[tile] = make_double2(gs, gz);
+      }
+    }
+  }
+}
+
+// Stage 2 for row tiles: channel c sums partial[(o*C + c)*tpr + j] over o, j (one warp per channel).
+__global__ void __launch_bounds__(kThreads) bwd_rows_finish_kernel(const double2* __restrict__ partial, long long outer,
+                                                                   int channels, long long tpr,
+                                                                   float* __restrict__ gs, float* __restrict__ gzp) {
+  const int lane = threadIdx.x & 31;
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= channels) return;
+  const long long cnt = outer * tpr;
+  double t0 = 0.0, t1 = 0.0;
+  for (long long i = lane; i < cnt; i += 32) {
+    const long long o = i / tpr, j = i - o * tpr;
+    const double2 v = partial[(o * channels + c) * tpr + j];
+    t0 += v.x;
+    t1 += v.y;
+  }
+  t0 = warp_sum(t0);
+  t1 = warp_sum(t1);
+  if (lane == 0) {
+    if (gs) gs[c] = (float)t0;
+    if (gzp) gzp[c] = (float)t1;
+  }
+}
+
+// Channel-last ([R, C], inner == 1): thread owns one channel, walks a block of rows.
+template <int ROUNDING>
+__global__ void __launch_bounds__(128) bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                       float* __restrict__ gx, const float* __restrict__ scale,
+                                                       const float* __restrict__ zero_point, long long R, int channels,
+                                                       long long rows_per_block, float qmin, float qmax, int rounding,
+                                                       double2* __restrict__ partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  QP p;
+  p.set(__ldg(scale + c), __ldg(zero_point + c));
+  p.qmin = qmin;
+  p.qmax = qmax;
+  const float lo_term = __fsub_rn(p.qmin, p.zp), hi_term = __fsub_rn(p.qmax, p.zp);
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+  BwdAcc a = {0.f, 0.f};
+  double d0 = 0.0, d1 = 0.0;
+  int k = 0;
+  for (long long r = r0; r < r1; ++r) {
+    const long long e = r * channels + c;
+    gx[e] = bwd1<ROUNDING>(__ldcs(x + e), __ldcs(gy + e), p, lo_term, hi_term, a, rounding);
+    if (++k == 256) {  // bound fp32 accumulation length
+      d0 += a.gs; d1 += a.gzp; a.gs = 0.f; a.gzp = 0.f; k = 0;
+    }
+  }
+  d0 += a.gs;
+  d1 += a.gzp;
+  if (partial) partial[(long long)blockIdx.y * channels + c] = make_double2(d0, d1);
+}
+
+__global__ void bwd_cols_finish_kernel(const double2* __restrict__ partial, int nblocks, int channels,
+                                       float* __restrict__ gs, float* __restrict__ gzp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  double t0 = 0.0, t1 = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    const double2 v = partial[(long long)b * channels + c];
+    t0 += v.x;
+    t1 += v.y;
+  }
+  if (gs) gs[c] = (float)t0;
+  if (gzp) gzp[c] = (float)t1;
+}
+
+static inline int persistent_grid(long long tiles, int ctas_per_sm) {
+  long long cap = (long long)sm_count() * ctas_per_sm;
+  if (tiles < 1) tiles = 1;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
+static inline long long cols_row_blocks(long long outer, long long channels) {
+  const long long gx = (channels + 127) / 128;
+  long long want = ((long long)sm_count() * 8 + gx - 1) / gx;
+  if (want > outer) want = outer;
+  if (want > 65535) want = 65535;
+  if (want < 1) want = 1;
+  const long long rpb = (outer + want - 1) / want;
+  return (outer + rpb - 1) / rpb;
+}
+
+static size_t bwd_ws_bytes(long long outer, long long channels, long long inner) {
+  if (outer <= 0 || channels <= 0 || inner <= 0) return 0;
+  if (inner == 1 && channels > 1) return (size_t)(cols_row_blocks(outer, channels) * channels) * sizeof(double2);
+  const long long tpr = (inner + kTile - 1) / kTile;
+  return (size_t)(outer * channels * tpr) * sizeof(double2);
+}
+
+static int bwd_dispatch(const float* x, const float* scale, const float* zp, const float* gy, float* gx, float* gs,
+                        float* gzp, long long outer, long long channels, long long inner, int qmin, int qmax,
+                        int rounding, void* workspace, size_t workspace_bytes, cudaStream_t st, const char* who) {
+  SB_REQUIRE(x && scale && zp && gy && gx, "%s: null pointer argument", who);
+  SB_REQUIRE(outer > 0 && channels > 0 && inner > 0, "%s: Kernel Failure, Tensor is empty: data", who);
+  SB_REQUIRE(qmin <= qmax, "%s: qmin > qmax", who);
+  SB_REQUIRE(rounding >= 0 && rounding <= 2, "%s: rounding must be 0, 1 or 2", who);
+  SB_REQUIRE(channels < (1LL << 31), "%s: too many channels", who);
+  const bool need_red = gs || gzp;
+  const size_t need = need_red ? bwd_ws_bytes(outer, channels, inner) : 0;
+  if (need_red && (!workspace || workspace_bytes < need)) {
+    set_error("%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes, need);
+    return SB200_E_WORKSPACE;
+  }
+  double2* partial = need_red ? (double2*)workspace : nullptr;
+  if (inner == 1 && channels > 1) {
+    const long long nb = cols_row_blocks(outer, channels);
+    const long long rpb = (outer + nb - 1) / nb;
+    const dim3 grid((unsigned)((channels + 127) / 128), (unsigned)nb);
+    if (rounding == 0)
+      bwd_cols_kernel<0><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, rounding, partial);
+    else
+      bwd_cols_kernel<-1><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, rounding, partial);
+    SB_LAUNCHED();
+    if (need_red) {
+      bwd_cols_finish_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(partial, (int)nb, (int)channels, gs, gzp);
+      SB_LAUNCHED();
+    }
+    return SB200_OK;
+  }
+  const long long rows = outer * channels;
+  const long long tpr = (inner + kTile - 1) / kTile;
+  const long long tiles = rows * tpr;
+  const bool cta_tile = inner >= 1024;
+#define SB_GO(CT_, R_)                                                                                   \
+  bwd_rows_kernel<CT_, R_><<<persistent_grid(CT_ ? tiles : (tiles + 7) / 8, 8), kThreads, 0, st>>>(     \
+      x, gy, gx, scale, zp, rows, inner, (int)channels, (float)qmin, (float)qmax, rounding, partial)
+  if (cta_tile) {
+    if (rounding == 0) SB_GO(true, 0); else SB_GO(true, -1);
+  } else {
+    if (rounding == 0) SB_GO(false, 0); else SB_GO(false, -1);
+  }
+#undef SB_GO
+  SB_LAUNCHED();
+  if (need_red) {
+    const long long warps = channels;
+    bwd_rows_finish_kernel<<<(unsigned)((warps * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+        partial, outer, (int)channels, tpr, gs, gzp);
+    SB_LAUNCHED();
+  }
+  return SB200_OK;
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+size_t sb200_qdq_bwd_workspace_bytes(int64_t outer, int64_t channels, int64_t inner) {
+  return bwd_ws_bytes(outer, channels, inner);
+}
+
+int sb200_qdq_pertensor_bwd(const float* x, const float* scale, const float* zero_point, const float* grad_y,
+                            float* grad_x, float* grad_scale, float* grad_zp, int64_t n, int qmin, int qmax,
+                            int rounding, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_dispatch(x, scale, zero_point, grad_y, grad_x, grad_scale, grad_zp, 1, 1, n, qmin, qmax, rounding,
+                      workspace, workspace_bytes, (cudaStream_t)stream, "sb200_qdq_pertensor_bwd");
+}
+
+int sb200_qdq_perchannel_bwd(const float* x, const float* scale, const float* zero_point, const float* grad_y,
+                             float* grad_x, float* grad_scale, float* grad_zp, int64_t outer, int64_t channels,
+                             int64_t inner, int qmin, int qmax, int rounding, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  return bwd_dispatch(x, scale, zero_point, grad_y, grad_x, grad_scale, grad_zp, outer, channels, inner, qmin, qmax,
+                      rounding, workspace, workspace_bytes, (cudaStream_t)stream, "sb200_qdq_perchannel_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// gptq.cu -- C-ABI entry points of the GPTQ int4 dequant-matmul and the SIMT / tcgen05 dispatch.
+//
+// Boundary replaced: cuda_kernel.vecquant4matmul / vecgroupquant4matmul
+// (large_language_models/llama/quantization/cuda/cuda_kernel.cpp:10-23,70,73) and their argument
+// checks (cuda_kernel_4bit.cu:44-60).
+#include "common.cuh"
+
+namespace sb200 {
+int gptq4_simt(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+               long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
+bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
+                        long long KW, int group_size);
+size_t gptq4_tc_workspace(long long M, long long K, long long N, int group_size);
+int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
+             long long K, long long N, long long KW, int group_size, void* workspace, size_t workspace_bytes,
+             cudaStream_t st);
+static int g_gptq_impl = 0;
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+int sb200_gptq4_set_impl(int impl) {
+  SB_REQUIRE(impl >= 0 && impl <= 2, "sb200_gptq4_set_impl: impl must be 0, 1 or 2 (got %d)", impl);
+  g_gptq_impl = impl;
+  return SB200_OK;
+}
+
+size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size) {
+  if (m <= 0 || k <= 0 || n <= 0) return 0;
+  if (group_size <= 0) group_size = (int)k;
+  return gptq4_tc_workspace(m, k, n, group_size);
+}
+
+int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+                       int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(x && qweight && out && scales && zeros, "sb200_gptq4_matmul: null pointer argument");
+  SB_REQUIRE(m > 0 && k > 0 && n > 0, "sb200_gptq4_matmul: empty operand (M=%lld K=%lld N=%lld)", (long long)m,
+             (long long)k, (long long)n);
+  SB_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && n < (1LL << 31), "sb200_gptq4_matmul: dimension too large");
+  SB_REQUIRE(qweight_rows >= (k + 7) / 8,
+             "sb200_gptq4_matmul: qweight has %lld rows, need ceil(K/8) = %lld", (long long)qweight_rows,
+             (long long)((k + 7) / 8));
+  if (group_size != 0) {
+    // cuda_kernel_4bit.cu:60
+    SB_REQUIRE(group_size > 0 && group_size % 128 == 0,
+               "only group_size divisible by 128 is supported in 4-bit quantization (got %d)", group_size);
+  } else {
+    group_size = (int)k;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  bool use_tc = false;
+  if (g_gptq_impl != 1) {
+    const bool ok = gptq4_tc_supported(x, qweight, out, m, k, n, qweight_rows, group_size) &&
+                    workspace && workspace_bytes >= gptq4_tc_workspace(m, k, n, group_size);
+    if (g_gptq_impl == 2) {
+      if (!ok) {
+        set_error("sb200_gptq4_matmul: tcgen05 path forced but shape/workspace unsupported (M=%lld K=%lld N=%lld gs=%d ws=%zu)",
+                  (long long)m, (long long)k, (long long)n, group_size, workspace_bytes);
+        return SB200_E_UNSUPPORTED;
+      }
+      use_tc = true;
+    } else {
+      use_tc = ok && m >= 32;
+    }
+  }
+  if (use_tc)
+    return gptq4_tc(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, workspace, workspace_bytes, st);
+  return gptq4_simt(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
+}
+
+}  // extern "C"

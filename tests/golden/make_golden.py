@@ -1,0 +1,236 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run once in the build container (the reference is not present on the GPU box):
+    python tests/golden/make_golden.py
+Outputs small ``.npz`` fixtures next to this file; they pin ``oracle/`` (tests/test_oracle_golden.py)
+and serve as known-answer inputs for the CUDA parity tests (tests/test_gpu_*.py).
+
+Reference entry points exercised (paths relative to /root/reference):
+  sparsebit/quantization/quantizers/quant_tensor.py:159-185  ort_fake_quant (CPU branch :181-184)
+  sparsebit/quantization/quantizers/quant_tensor.py:128-156  trt_fake_quant (CPU branch :154-155)
+  sparsebit/quantization/quantizers/base.py:33-39,66-68      Quantizer.update_observer / calc_qparams
+  sparsebit/quantization/observers/{minmax,mse,percentile,kl_histogram}.py
+  sparsebit/sparse/sparsers/l1norm.py:14-26                  unstructured mask
+  large_language_models/llama/quantization/utils/quant.py    Quantizer.find_params, QuantLinear.pack
+  large_language_models/llama/quantization/test_cuda_kernel.py:21-47  known-answer construction
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _ref_import as R  # noqa: E402
+
+R.install_shims()
+from sparsebit.quantization.common import Backend  # noqa: E402
+from sparsebit.quantization.quantizers import build_quantizer  # noqa: E402
+from sparsebit.quantization.quantizers.quant_tensor import ort_fake_quant, trt_fake_quant  # noqa: E402
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def gen_qdq():
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    cases = []
+    specs = [
+        # name, shape, qscheme, bit, target, layout
+        ("pt_sym8", (2, 3, 9, 7), "per-tensor-symmetric", 8, "feature", "NCHW"),
+        ("pt_aff8", (2, 3, 9, 7), "per-tensor-affine", 8, "feature", "NCHW"),
+        ("pt_aff4", (5, 37), "per-tensor-affine", 4, "feature", "NCHW"),
+        ("pc_w_sym8", (6, 4, 3, 3), "per-channel-symmetric", 8, "weight", None),
+        ("pc_w_aff4", (7, 11), "per-channel-affine", 4, "weight", None),
+        ("pc_a_nchw_sym8", (2, 5, 7, 7), "per-channel-symmetric", 8, "feature", "NCHW"),
+        ("pc_a_nlc_aff8", (3, 5, 8), "per-channel-affine", 8, "feature", "NLC"),
+        ("pc_a_nlc_sym8_c7", (2, 6, 7), "per-channel-symmetric", 8, "feature", "NLC"),
+    ]
+    for name, shape, scheme, bit, target, layout in specs:
+        cfg = R.make_cfg(scheme, bit, target, "minmax", layout or "NCHW")
+        q = build_quantizer(cfg)
+        q.set_backend(Backend.VIRTUAL)
+        x = torch.randn(shape, generator=g) * 1.7
+        if "aff" in name and target == "feature":
+            x = torch.relu(x) + 0.0  # post-ReLU style, affine
+        # exact ties and out-of-range values
+        flat = x.reshape(-1)
+        q.update_observer(x)
+        scale, zp = q.calc_qparams()
+        s_flat = scale.reshape(-1)
+        flat[0] = 0.5 * s_flat[0]
+        flat[1] = 1.5 * s_flat[0]
+        flat[2] = -2.5 * s_flat[0]
+        flat[3] = 1e4
+        flat[4] = -1e4
+        # fractional zero points (learned LSQ+ style), incl. exact .5 (Q1)
+        zp2 = zp.clone()
+        if "aff" in name:
+            zp2 = zp2 + 0.5
+        y = ort_fake_quant(x, scale, zp2, q.qdesc)
+        cases.append(name)
+        out[name + "_x"] = x.numpy()
+        out[name + "_scale"] = scale.reshape(-1).numpy()
+        out[name + "_zp"] = zp2.reshape(-1).numpy()
+        out[name + "_y"] = y.numpy()
+        out[name + "_meta"] = np.array([q.qdesc.qmin, q.qdesc.qmax, q.qdesc.ch_axis, int(q.qdesc.is_perchannel)])
+        if "sym" in name:
+            yt = trt_fake_quant(x, scale, zp, q.qdesc)
+            out[name + "_ytrt"] = yt.numpy()
+    out["cases"] = np.array(cases)
+    save("qdq", **out)
+
+
+def gen_observers():
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    cases = []
+    specs = [
+        # name, observer, scheme, bit, target, layout, shapes(batches), alpha
+        ("minmax_pt_sym", "minmax", "per-tensor-symmetric", 8, "feature", "NCHW", [(2, 3, 8, 8)] * 3, 1e-3),
+        ("minmax_pt_aff", "minmax", "per-tensor-affine", 8, "feature", "NCHW", [(2, 3, 8, 8)] * 2, 1e-3),
+        ("minmax_pc_w", "minmax", "per-channel-symmetric", 8, "weight", None, [(6, 4, 3, 3)], 1e-3),
+        ("minmax_pc_nchw", "minmax", "per-channel-affine", 8, "feature", "NCHW", [(4, 5, 7, 7)], 1e-3),
+        ("minmax_pc_nlc", "minmax", "per-channel-symmetric", 8, "feature", "NLC", [(3, 9, 8)], 1e-3),
+        ("mse_pt_sym", "mse", "per-tensor-symmetric", 8, "feature", "NCHW", [(2, 3, 16, 16)] * 2, 1e-3),
+        ("mse_pt_aff4", "mse", "per-tensor-affine", 4, "feature", "NCHW", [(2, 3, 16, 16)] * 2, 1e-3),
+        ("pct_pt_sym", "percentile", "per-tensor-symmetric", 8, "feature", "NCHW", [(4, 3, 16, 16)] * 2, 1e-2),
+        ("pct_pt_aff", "percentile", "per-tensor-affine", 8, "feature", "NCHW", [(4, 3, 16, 16)] * 2, 1e-3),
+        ("pct_pc_w", "percentile", "per-channel-symmetric", 8, "weight", None, [(5, 64, 3, 3)], 2e-2),
+        ("kl_pt_sym", "kl_histogram", "per-tensor-symmetric", 8, "feature", "NCHW", [(2, 3, 16, 16)] * 2, 1e-3),
+        ("kl_pt_aff4", "kl_histogram", "per-tensor-affine", 4, "feature", "NCHW", [(2, 3, 16, 16)] * 2, 1e-3),
+    ]
+    for name, obs, scheme, bit, target, layout, shapes, alpha in specs:
+        cfg = R.make_cfg(scheme, bit, target, obs, layout or "NCHW", alpha=alpha)
+        q = build_quantizer(cfg)
+        q.set_backend(Backend.VIRTUAL)
+        xs = []
+        for i, shp in enumerate(shapes):
+            x = torch.randn(shp, generator=g) * (1.0 + 0.3 * i)
+            if "aff" in name and target == "feature":
+                x = torch.relu(x)
+            xs.append(x)
+            q.update_observer(x)
+        scale, zp = q.calc_qparams()
+        cases.append(name)
+        for i, x in enumerate(xs):
+            out[f"{name}_x{i}"] = x.numpy()
+        out[name + "_nb"] = np.array(len(xs))
+        out[name + "_scale"] = scale.reshape(-1).numpy()
+        out[name + "_zp"] = zp.reshape(-1).numpy()
+        if obs != "mse":
+            out[name + "_min"] = q.observer.min_val.reshape(-1).numpy()
+            out[name + "_max"] = q.observer.max_val.reshape(-1).numpy()
+        out[name + "_meta"] = np.array(
+            [q.qdesc.qmin, q.qdesc.qmax, q.qdesc.ch_axis, int(q.qdesc.is_perchannel), int(q.qdesc.is_symmetric), bit]
+        )
+        out[name + "_alpha"] = np.array(alpha)
+    out["cases"] = np.array(cases)
+    # torch.histc known answers (ATen CPU), incl. values exactly on edges
+    x = torch.randn(5000, generator=g) * 2.0
+    am = x.abs().max()
+    edges = torch.linspace(-am.item(), am.item(), 2049)
+    x[:2049] = edges  # every edge value itself
+    x[2049] = am
+    x[2050] = -am
+    h = torch.histc(x, bins=2048, min=-am.item(), max=am.item())
+    out["histc_x"] = x.numpy()
+    out["histc_absmax"] = am.numpy()
+    out["histc_counts"] = h.numpy()
+    out["histc_edges"] = edges.numpy()
+    save("observers", **out)
+
+
+def gen_sparse():
+    from sparsebit.sparse.sparsers import build_sparser
+
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    cases = []
+    for name, shape, ratio in [
+        ("conv_r50", (8, 4, 3, 3), 0.5),
+        ("lin_r25", (10, 33), 0.25),
+        ("lin_r75", (10, 33), 0.75),
+        ("lin_r100", (6, 5), 1.0),
+        ("ties", (4, 16), 0.5),
+        ("r0", (3, 5), 0.0),
+    ]:
+        cfg = R._CfgNode({"SPARSER": {"TYPE": "unstructed", "STRATEGY": "l1norm", "RATIO": ratio}})
+        sp = build_sparser(cfg, opr=None)
+        w = torch.randn(shape, generator=g)
+        if name == "ties":
+            w = torch.round(w * 2) / 2  # many equal magnitudes
+        mask = sp.calc_mask(w)
+        cases.append(name)
+        out[name + "_w"] = w.numpy()
+        out[name + "_mask"] = mask.numpy()
+        out[name + "_masked"] = (w * mask).numpy()
+        out[name + "_ratio"] = np.array(ratio)
+    out["cases"] = np.array(cases)
+    save("sparse", **out)
+
+
+def gen_gptq():
+    # stub the CUDA loader imported by utils/quant.py:5
+    qroot = os.path.join(R.REFERENCE_ROOT, "large_language_models/llama/quantization")
+    sys.path.insert(0, qroot)
+    stub = types.ModuleType("utils.load_cuda_kernel")
+    stub.cuda_kernel = None
+    sys.modules["utils.load_cuda_kernel"] = stub
+    from utils.quant import QuantLinear, Quantizer, quantize  # noqa: E402
+
+    torch.manual_seed(7)
+    out = {}
+    cases = []
+    # (name, B-shape, M(in), N(out), GS) -- scaled-down mirrors of test_cuda_kernel.py:50-126
+    for name, bshape, M, N, GS in [
+        ("single_block", (1,), 128, 64, -1),
+        ("single_irregular", (1,), 127, 61, -1),
+        ("irregular_b31", (31,), 333, 251, -1),
+        ("tokens_4x8", (4, 8), 256, 96, -1),
+        ("group128_b29", (29,), 512, 136, 128),
+        ("group384_b4", (4,), 768, 72, 384),
+        ("group128_m130", (130,), 256, 128, 128),
+    ]:
+        layer = torch.nn.Linear(M, N)
+        vec = torch.randn(bshape + (M,))
+        quantizer = Quantizer()
+        quantizer.configure(bit=4, perchannel=True, sym=False, mse=False)
+        quantizer.find_params(layer.weight.data, weight=True, groupsize=GS)
+        layer.weight.data = quantize(
+            layer.weight.data.view(-1, M if GS == -1 else GS),
+            quantizer.scale.view(-1, 1),
+            quantizer.zero.view(-1, 1),
+            quantizer.maxq,
+        ).view(N, M)
+        w_orig_scale, w_orig_zero = quantizer.scale.clone(), quantizer.zero.clone()
+        ql = QuantLinear(M, N, bit=4, groupsize=GS)
+        ql.pack(layer, quantizer.scale, quantizer.zero)
+        with torch.no_grad():
+            gt = layer(vec)
+        cases.append(name)
+        out[name + "_x"] = vec.numpy()
+        out[name + "_wdq"] = layer.weight.data.numpy()
+        out[name + "_qweight"] = ql.qweight.numpy()
+        out[name + "_scales"] = ql.scales.reshape(N, -1).numpy()
+        out[name + "_zeros"] = ql.zeros.reshape(N, -1).numpy()
+        out[name + "_zero_int"] = w_orig_zero.reshape(N, -1).numpy()
+        out[name + "_bias"] = ql.bias.detach().numpy()
+        out[name + "_gt"] = gt.numpy()
+        out[name + "_gs"] = np.array(GS)
+    out["cases"] = np.array(cases)
+    save("gptq", **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    gen_qdq()
+    gen_observers()
+    gen_sparse()
+    gen_gptq()

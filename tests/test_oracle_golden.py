@@ -1,0 +1,100 @@
+"""CPU: pin the numpy oracle against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  Integer / mask paths bit-exact, float rescale bit-exact too
+(same IEEE op sequence), MSE argmin identical, KL threshold identical."""
+import numpy as np
+import pytest
+
+from oracle import gptq as ogptq
+from oracle import observers as oobs
+from oracle import qdq as oqdq
+from oracle import sparse as osparse
+
+
+def _eq_bits(a, b):
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    # treat +0 / -0 as equal, NaN == NaN
+    return np.array_equal(np.where(a == 0, 0.0, a), np.where(b == 0, 0.0, b), equal_nan=True)
+
+
+def test_qdq_matches_reference(golden):
+    g = golden("qdq")
+    for name in g["cases"]:
+        qmin, qmax, ch_axis, _ = g[name + "_meta"]
+        y = oqdq.qdq(g[name + "_x"], g[name + "_scale"], g[name + "_zp"], int(qmin), int(qmax), int(ch_axis))
+        assert _eq_bits(y, g[name + "_y"]), name
+        if name + "_ytrt" in g.files:  # symmetric: TensorRT-style branch equals zp == 0
+            y0 = oqdq.qdq(g[name + "_x"], g[name + "_scale"], np.zeros_like(g[name + "_zp"]), int(qmin), int(qmax), int(ch_axis))
+            assert _eq_bits(y0, g[name + "_ytrt"]), name
+
+
+def _batches(g, name):
+    return [g[f"{name}_x{i}"] for i in range(int(g[name + "_nb"]))]
+
+
+@pytest.mark.parametrize("kind", ["minmax", "pct", "kl", "mse"])
+def test_observers_match_reference(golden, kind):
+    g = golden("observers")
+    seen = 0
+    for name in g["cases"]:
+        if not name.startswith(kind):
+            continue
+        seen += 1
+        qmin, qmax, ch_axis, perch, sym, bit = (int(v) for v in g[name + "_meta"])
+        xs = _batches(g, name)
+        if kind == "minmax":
+            mn, mx = oobs.minmax(xs, bool(perch), ch_axis)
+        elif kind == "pct":
+            mn, mx = oobs.percentile(xs, float(g[name + "_alpha"]), bool(perch), ch_axis)
+        elif kind == "kl":
+            mn, mx = oobs.kl_histogram(xs, bit)
+        if kind == "mse":
+            s, z, _ = oobs.mse(xs, qmin, qmax, bool(sym), bool(perch), ch_axis)
+        else:
+            assert _eq_bits(np.reshape(mn, -1), g[name + "_min"]), name
+            assert _eq_bits(np.reshape(mx, -1), g[name + "_max"]), name
+            s, z = oobs.calc_qparams_with_minmax(mn, mx, qmin, qmax, bool(sym))
+        assert _eq_bits(np.reshape(s, -1), g[name + "_scale"]), name
+        assert _eq_bits(np.reshape(z, -1), g[name + "_zp"]), name
+    assert seen > 0
+
+
+def test_histc_matches_aten(golden):
+    g = golden("observers")
+    am = float(g["histc_absmax"])
+    h = oobs.histc(g["histc_x"], 2048, -am, am)
+    assert np.array_equal(h, g["histc_counts"].astype(np.int64))
+
+
+def test_sparse_matches_reference(golden):
+    g = golden("sparse")
+    for name in g["cases"]:
+        w, ratio = g[name + "_w"], float(g[name + "_ratio"])
+        m = osparse.l1_unstructured_mask(w, ratio)
+        assert np.array_equal(np.asarray(m).astype(np.float32), g[name + "_mask"].astype(np.float32)), name
+        assert _eq_bits(osparse.mask_apply(w, m), g[name + "_masked"]), name
+
+
+def test_gptq_matches_reference(golden):
+    g = golden("gptq")
+    for name in g["cases"]:
+        gs = int(g[name + "_gs"])
+        x, qw = g[name + "_x"], g[name + "_qweight"]
+        n = qw.shape[1]
+        k = x.shape[-1]
+        # packed integers decode back to the dequantised weights the reference's ground truth uses
+        s, z = g[name + "_scales"], g[name + "_zeros"]
+        q = ogptq.unpack_int4(qw, k).astype(np.float32)
+        gsz = k if gs == -1 else gs
+        gi = np.arange(k) // gsz
+        w = (s.T[gi] * q - z.T[gi]).T  # [N, K]
+        np.testing.assert_allclose(w, g[name + "_wdq"], rtol=0, atol=2e-7)
+        bias = np.broadcast_to(g[name + "_bias"], x.shape[:-1] + (n,))
+        y = ogptq.dequant_matmul(x, qw, bias, s, z, 0 if gs == -1 else gs)
+        # reference pin: test_cuda_kernel.py:47  rtol = atol = 1e-5 against Linear(dequantised W)
+        np.testing.assert_allclose(y, g[name + "_gt"], rtol=1e-5, atol=1e-5)
+        # the oracle's own find_params / pack reproduce the reference's packed tensors
+        s2, z2 = ogptq.find_params_int4(g[name + "_wdq"], gs)
+        qw2, sc2, zr2 = ogptq.pack_int4(g[name + "_wdq"], s2, z2)
+        # (dequantised weights re-quantise onto the same grid)
+        np.testing.assert_allclose(sc2, s, rtol=1e-6, atol=0)
