@@ -1,0 +1,296 @@
+"""Tensor-level wrappers over the C-ABI: torch is used for device memory and streams only.
+
+Every function takes CUDA fp32 tensors, launches on ``torch.cuda.current_stream()`` of the
+tensor's device and never synchronises the host.  Non-fp32 / empty / CPU inputs raise
+``RuntimeError`` like the reference's pybind modules do (torch_extensions/common.cuh:45-55).
+"""
+import torch
+
+from . import _lib
+from ._lib import SparsebitB200Error, check
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise SparsebitB200Error(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise SparsebitB200Error(f"{name}: expected a CUDA tensor (sparsebit_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise SparsebitB200Error(f"Kernel Failure, Invalid dtype of Input tensor: {name}(Expect to be {dtype})")
+    if t.numel() == 0:
+        raise SparsebitB200Error(f"Kernel Failure, Tensor is empty: {name}")
+    if not t.is_contiguous():
+        raise SparsebitB200Error(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def channel_geometry(shape, ch_axis):
+    """[outer, C, inner] view used by the per-channel kernels (fake_quant_tensor.cu:203-208)."""
+    ch_axis = ch_axis % len(shape)
+    outer = 1
+    for d in shape[:ch_axis]:
+        outer *= int(d)
+    inner = 1
+    for d in shape[ch_axis + 1 :]:
+        inner *= int(d)
+    return outer, int(shape[ch_axis]), inner
+
+
+# ----------------------------------------------------------------------------- QDQ forward
+def qdq_pertensor(x, scale, zero_point, qmin, qmax, rounding=0, out=None):
+    lib = _lib.load()
+    _req(x, "data"), _req(scale, "scale"), _req(zero_point, "zero_point")
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        check(lib.sb200_qdq_pertensor_fwd(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), out.data_ptr(),
+                                          x.numel(), int(qmin), int(qmax), int(rounding), _stream(x)))
+    return out
+
+
+def qdq_perchannel(x, scale, zero_point, qmin, qmax, ch_axis, rounding=0, out=None):
+    lib = _lib.load()
+    _req(x, "data"), _req(scale, "scale"), _req(zero_point, "zero_point")
+    outer, c, inner = channel_geometry(x.shape, ch_axis)
+    if scale.numel() != c or zero_point.numel() != c:
+        raise SparsebitB200Error(f"per-channel qparams need {c} elements (got {scale.numel()}, {zero_point.numel()})")
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        check(lib.sb200_qdq_perchannel_fwd(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), out.data_ptr(),
+                                           outer, c, inner, int(qmin), int(qmax), int(rounding), _stream(x)))
+    return out
+
+
+def qdq_stats_pertensor(x, scale, zero_point, qmin, qmax, state, rounding=0, out=None):
+    """Fused QDQ + running min/max of x.  ``state``: int32[2] tensor from ``minmax_new(1)``."""
+    lib = _lib.load()
+    _req(x, "data"), _req(scale, "scale"), _req(zero_point, "zero_point")
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        check(lib.sb200_qdq_stats_pertensor_fwd(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), out.data_ptr(),
+                                                state.data_ptr(), x.numel(), int(qmin), int(qmax), int(rounding), _stream(x)))
+    return out
+
+
+# ----------------------------------------------------------------------------- STE backward
+def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, rounding=0, need_gs=True, need_gzp=True):
+    """Returns (gx, gs, gzp); gs / gzp shaped like scale / zero_point (zeros when not requested,
+    like the reference which returns zeros_like, fake_quant_tensor.cu:147-149)."""
+    lib = _lib.load()
+    _req(x, "data"), _req(scale, "scale"), _req(zero_point, "zero_point"), _req(grad_y, "grad")
+    if grad_y.shape != x.shape:
+        raise SparsebitB200Error("grad_y must have the shape of data")
+    gx = torch.empty_like(x)
+    gs = torch.zeros_like(scale)
+    gzp = torch.zeros_like(zero_point)
+    if ch_axis is None:
+        outer, c, inner = 1, 1, x.numel()
+    else:
+        outer, c, inner = channel_geometry(x.shape, ch_axis)
+    need = need_gs or need_gzp
+    ws_bytes = int(lib.sb200_qdq_bwd_workspace_bytes(outer, c, inner)) if need else 0
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        if ch_axis is None:
+            check(lib.sb200_qdq_pertensor_bwd(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), grad_y.data_ptr(),
+                                              gx.data_ptr(), gs.data_ptr() if need_gs else None,
+                                              gzp.data_ptr() if need_gzp else None, x.numel(), int(qmin), int(qmax),
+                                              int(rounding), ws.data_ptr(), ws_bytes, _stream(x)))
+        else:
+            check(lib.sb200_qdq_perchannel_bwd(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), grad_y.data_ptr(),
+                                               gx.data_ptr(), gs.data_ptr() if need_gs else None,
+                                               gzp.data_ptr() if need_gzp else None, outer, c, inner, int(qmin),
+                                               int(qmax), int(rounding), ws.data_ptr(), ws_bytes, _stream(x)))
+    return gx, gs, gzp
+
+
+# ----------------------------------------------------------------------------- MinMax
+def minmax_new(channels, device):
+    """Fresh running min/max state: int32[2*C] (bit pattern of the uint32 ordered keys)."""
+    lib = _lib.load()
+    st = torch.empty(2 * channels, dtype=torch.int32, device=device)
+    with torch.cuda.device(st.device):
+        check(lib.sb200_minmax_init(st.data_ptr(), channels, _stream(st)))
+    return st
+
+
+def minmax_update(x, state, ch_axis=None):
+    lib = _lib.load()
+    _req(x, "data")
+    with torch.cuda.device(x.device):
+        if ch_axis is None:
+            check(lib.sb200_observe_minmax(x.data_ptr(), x.numel(), state.data_ptr(), _stream(x)))
+        else:
+            outer, c, inner = channel_geometry(x.shape, ch_axis)
+            if state.numel() != 2 * c:
+                raise SparsebitB200Error(f"minmax state holds {state.numel() // 2} channels, data has {c}")
+            check(lib.sb200_observe_minmax_perchannel(x.data_ptr(), outer, c, inner, state.data_ptr(), _stream(x)))
+
+
+def minmax_read(state):
+    lib = _lib.load()
+    c = state.numel() // 2
+    mn = torch.empty(c, dtype=torch.float32, device=state.device)
+    mx = torch.empty(c, dtype=torch.float32, device=state.device)
+    with torch.cuda.device(state.device):
+        check(lib.sb200_minmax_read(state.data_ptr(), c, mn.data_ptr(), mx.data_ptr(), _stream(state)))
+    return mn, mx
+
+
+# ----------------------------------------------------------------------------- histogram / MSE
+def hist_update(x, range_lo_hi, counts):
+    """counts (int64[bins]) += histc(x, bins, lo, hi); ``range_lo_hi``: device float32[2]."""
+    lib = _lib.load()
+    _req(x, "data"), _req(range_lo_hi, "range")
+    with torch.cuda.device(x.device):
+        check(lib.sb200_observe_hist(x.data_ptr(), x.numel(), range_lo_hi.data_ptr(), counts.numel(), counts.data_ptr(), _stream(x)))
+
+
+def mse_sweep(x2d, cand_scale, cand_zp, qmin, qmax, sse):
+    """sse[rows, ncand] (fp64) += sum_j (x - qdq_i(x))^2 for every candidate i; x2d: [rows, row_len]."""
+    lib = _lib.load()
+    _req(x2d, "data"), _req(cand_scale, "cand_scale"), _req(cand_zp, "cand_zp")
+    rows, row_len = x2d.shape
+    ncand = cand_scale.numel() // rows
+    ws_bytes = int(lib.sb200_mse_workspace_bytes(rows, row_len, ncand))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        check(lib.sb200_observe_mse_sweep(x2d.data_ptr(), rows, row_len, cand_scale.data_ptr(), cand_zp.data_ptr(), ncand,
+                                          int(qmin), int(qmax), sse.data_ptr(), ws.data_ptr(), ws_bytes, _stream(x2d)))
+
+
+# ----------------------------------------------------------------------------- radix select
+class RadixSelect:
+    """Exact order statistics over one or more device tensors (3 passes x 4 B/elem).
+
+    rows x ntargets_per_row independent selections; ``add_pass(p, tensors)`` accumulates the
+    digit histograms of pass p for every tensor (each viewed as [rows, row_len]); an optional
+    ``reduce`` callback (SUM all-reduce across GPUs) runs between histogram and scan."""
+
+    def __init__(self, rows, ntargets_per_row, device, key_mode=0):
+        self.lib = _lib.load()
+        self.rows, self.ntpr, self.key_mode = rows, ntargets_per_row, key_mode
+        n = rows * ntargets_per_row
+        self.sel = torch.zeros(n * _lib.SELECT_STATE_WORDS, dtype=torch.int64, device=device)
+        self.hist = torch.zeros(n * _lib.SELECT_BINS, dtype=torch.int64, device=device)
+        self.counts = torch.zeros(rows * 2, dtype=torch.int64, device=device)
+        with torch.cuda.device(device):
+            check(self.lib.sb200_select_init(self.sel.data_ptr(), self.hist.data_ptr(), n, None, _stream(self.sel)))
+
+    def set_ranks(self, ranks):
+        """ranks: int64 device tensor [rows * ntpr] of 0-based ranks."""
+        self.sel.view(-1, _lib.SELECT_STATE_WORDS)[:, 1] = ranks.to(torch.int64)
+
+    def hist_pass(self, p, x2d, with_counts=False):
+        _req(x2d, "data")
+        rows, row_len = x2d.shape
+        with torch.cuda.device(x2d.device):
+            if with_counts and p == 0:
+                check(self.lib.sb200_select_hist_counts(x2d.data_ptr(), rows, row_len, self.ntpr, self.sel.data_ptr(),
+                                                        self.hist.data_ptr(), p, self.key_mode, self.counts.data_ptr(), _stream(x2d)))
+            else:
+                check(self.lib.sb200_select_hist(x2d.data_ptr(), rows, row_len, self.ntpr, self.sel.data_ptr(),
+                                                 self.hist.data_ptr(), p, self.key_mode, _stream(x2d)))
+
+    def percentile_ranks(self, total, alpha):
+        """total: int64 device tensor [rows] (elements per row incl. NaN)."""
+        with torch.cuda.device(self.sel.device):
+            check(self.lib.sb200_percentile_ranks(self.counts.data_ptr(), total.data_ptr(), self.rows, float(alpha),
+                                                  self.sel.data_ptr(), _stream(self.sel)))
+
+    def scan(self, p):
+        with torch.cuda.device(self.sel.device):
+            check(self.lib.sb200_select_scan(self.sel.data_ptr(), self.hist.data_ptr(), self.rows, self.ntpr, p, _stream(self.sel)))
+
+    def values(self):
+        n = self.rows * self.ntpr
+        out = torch.empty(n, dtype=torch.float32, device=self.sel.device)
+        with torch.cuda.device(self.sel.device):
+            check(self.lib.sb200_select_read(self.sel.data_ptr(), n, self.key_mode, out.data_ptr(), _stream(self.sel)))
+        return out
+
+
+def kth_value(x, k, key_mode=0):
+    """k-th smallest (0-based) of a flat tensor, exact; key_mode 1 ranks |x|."""
+    rs = RadixSelect(1, 1, x.device, key_mode)
+    rs.set_ranks(torch.tensor([k], dtype=torch.int64, device=x.device))
+    x2 = x.reshape(1, -1)
+    for p in range(3):
+        rs.hist_pass(p, x2)
+        rs.scan(p)
+    return rs.values()
+
+
+# ----------------------------------------------------------------------------- sparser
+def mask_gt(w, thresh):
+    lib = _lib.load()
+    _req(w, "weight"), _req(thresh, "thresh")
+    mask = torch.empty(w.shape, dtype=torch.bool, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.sb200_mask_gt(w.data_ptr(), thresh.data_ptr(), mask.data_ptr(), w.numel(), _stream(w)))
+    return mask
+
+
+def mask_apply(w, mask, out=None):
+    lib = _lib.load()
+    _req(w, "weight")
+    if mask.shape != w.shape or not mask.is_cuda or not mask.is_contiguous():
+        raise SparsebitB200Error("mask must be a contiguous CUDA tensor of the weight's shape")
+    out = torch.empty_like(w) if out is None else out
+    with torch.cuda.device(w.device):
+        if mask.dtype in (torch.bool, torch.uint8):
+            check(lib.sb200_mask_apply(w.data_ptr(), mask.data_ptr(), out.data_ptr(), w.numel(), _stream(w)))
+        elif mask.dtype == torch.float32:
+            check(lib.sb200_mask_apply_f32(w.data_ptr(), mask.data_ptr(), out.data_ptr(), w.numel(), _stream(w)))
+        else:
+            raise SparsebitB200Error(f"unsupported mask dtype {mask.dtype}")
+    return out
+
+
+def mask_apply_qdq_perchannel(w, mask, scale, zero_point, qmin, qmax, ch_axis=0, rounding=0, out=None):
+    lib = _lib.load()
+    _req(w, "weight"), _req(scale, "scale"), _req(zero_point, "zero_point")
+    if mask.dtype not in (torch.bool, torch.uint8) or mask.shape != w.shape or not mask.is_contiguous():
+        raise SparsebitB200Error("fused mask+QDQ needs a contiguous bool mask of the weight's shape")
+    outer, c, inner = channel_geometry(w.shape, ch_axis)
+    out = torch.empty_like(w) if out is None else out
+    with torch.cuda.device(w.device):
+        check(lib.sb200_mask_apply_qdq_perchannel(w.data_ptr(), mask.data_ptr(), scale.data_ptr(), zero_point.data_ptr(),
+                                                  out.data_ptr(), outer, c, inner, int(qmin), int(qmax), int(rounding), _stream(w)))
+    return out
+
+
+# ----------------------------------------------------------------------------- GPTQ
+_gptq_ws = {}
+
+
+def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0):
+    """In-place ``out += x @ dequant(qweight)`` (vecquant4matmul contract, cuda_kernel.cpp:10-23)."""
+    lib = _lib.load()
+    _req(x, "inp1"), _req(out, "out"), _req(scales, "scales"), _req(zeros, "zeros")
+    _req(qweight, "inp2", torch.int32)
+    if x.dim() < 2:
+        raise SparsebitB200Error("input1 must be with dimension >= 2")  # cuda_kernel_4bit.cu:44
+    if qweight.dim() != 2:
+        raise SparsebitB200Error("input2 must be with dimension == 2")  # cuda_kernel_4bit.cu:48
+    k = x.shape[-1]
+    m = x.numel() // k
+    n = qweight.shape[1]
+    if out.shape[-1] != n:
+        raise SparsebitB200Error("output channel must be the same with input2 out_channel")  # :52
+    ws_bytes = int(lib.sb200_gptq4_workspace_bytes(m, k, n, int(group_size)))
+    ws = None
+    if ws_bytes:
+        key = (x.device, torch.cuda.current_stream(x.device).cuda_stream)
+        ws = _gptq_ws.get(key)
+        if ws is None or ws.numel() < ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            _gptq_ws[key] = ws
+    with torch.cuda.device(x.device):
+        check(lib.sb200_gptq4_matmul(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(), zeros.data_ptr(),
+                                     m, k, n, qweight.shape[0], int(group_size), ws.data_ptr() if ws is not None else None,
+                                     ws_bytes, _stream(x)))
+    return out

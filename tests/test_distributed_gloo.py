@@ -1,0 +1,93 @@
+"""CPU, world_size 2, gloo: the sharded-calibration statistic merge (sparsebit_b200/distributed.py)
+-- packed MAX all-reduce of order-preserving min/max keys and packed SUM all-reduce."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _enc(f):
+    b = np.asarray(f, dtype=np.float32).view(np.uint32)
+    k = np.where(b & 0x80000000, ~b, b | 0x80000000).astype(np.uint32)
+    return k
+
+
+def _state(mins, maxs):
+    keys = np.stack([_enc(mins), _enc(maxs)], axis=1).reshape(-1)
+    return torch.from_numpy(keys.view(np.int32).copy())
+
+
+def _dec(state):
+    k = state.numpy().view(np.uint32)
+    b = np.where(k & 0x80000000, k & 0x7FFFFFFF, ~k).astype(np.uint32)
+    return b.view(np.float32).reshape(-1, 2)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparsebit_b200 import distributed as sbdist
+
+    sbdist.enable()
+    rng = np.random.default_rng(100 + rank)
+    mins = [rng.standard_normal(1).astype(np.float32) - 1, rng.standard_normal(5).astype(np.float32) - 1]
+    maxs = [rng.standard_normal(1).astype(np.float32) + 1, rng.standard_normal(5).astype(np.float32) + 1]
+    if rank == 1:
+        mins[1][2] = -0.0
+        maxs[1][3] = 1e-30
+    states = [_state(mins[0], maxs[0]), _state(mins[1], maxs[1])]
+    sbdist.sync_minmax(states)
+    hist = torch.arange(8, dtype=torch.int64) * (rank + 1)
+    sse = torch.full((2, 3), 0.5 + rank, dtype=torch.float64)
+    sbdist.sync_sum([hist])
+    sbdist.sync_sum([sse])
+    if rank == 0:
+        torch.save({"s0": _dec(states[0]), "s1": _dec(states[1]), "hist": hist, "sse": sse}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stat_allreduce_world2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    exp_min, exp_max = [], []
+    per_rank = []
+    for rank in range(2):
+        rng = np.random.default_rng(100 + rank)
+        mins = [rng.standard_normal(1).astype(np.float32) - 1, rng.standard_normal(5).astype(np.float32) - 1]
+        maxs = [rng.standard_normal(1).astype(np.float32) + 1, rng.standard_normal(5).astype(np.float32) + 1]
+        if rank == 1:
+            mins[1][2] = -0.0
+            maxs[1][3] = 1e-30
+        per_rank.append((mins, maxs))
+    for i, key in enumerate(["s0", "s1"]):
+        mn = np.minimum(per_rank[0][0][i], per_rank[1][0][i])
+        mx = np.maximum(per_rank[0][1][i], per_rank[1][1][i])
+        np.testing.assert_array_equal(got[key][:, 0], mn)
+        np.testing.assert_array_equal(got[key][:, 1], mx)
+    assert torch.equal(got["hist"], torch.arange(8, dtype=torch.int64) * 3)
+    assert torch.equal(got["sse"], torch.full((2, 3), 2.0, dtype=torch.float64))
+
+
+def test_pack_unpack_roundtrip_without_process_group():
+    from sparsebit_b200 import distributed as sbdist
+
+    st = [_state(np.float32([-3.5]), np.float32([2.25])), _state(np.float32([-1, 0.0, 5]), np.float32([1, 0.0, 9]))]
+    before = [s.clone() for s in st]
+    packed = sbdist.pack_minmax(st)
+    assert packed.dtype == torch.int64 and packed.numel() == 8
+    sbdist.unpack_minmax(packed, st)
+    for a, b in zip(st, before):
+        assert torch.equal(a, b)
+    assert not sbdist.active()
+    sbdist.sync_minmax(st)  # no-op when not enabled
+    sbdist.sync_sum([torch.zeros(2)])

@@ -1,0 +1,109 @@
+"""GPU parity: GPTQ int4 dequant-matmul through the ``cuda_kernel`` mirror / QuantLinear vs the
+reference's known-answer construction (test_cuda_kernel.py: rtol = atol = 1e-5 against
+Linear(dequantised W), fp32, TF32 off) and the fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import dev, t
+from oracle import gptq as ogptq
+from sparsebit_b200 import _lib
+from sparsebit_b200.gptq import QuantLinear, cuda_kernel, find_params_int4
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-5, atol=1e-5)  # test_cuda_kernel.py:47
+
+
+def _run(x, qw, bias, scales, zeros, gs):
+    y = t(np.broadcast_to(bias, x.shape[:-1] + (qw.shape[1],)).copy())
+    if gs == -1:
+        cuda_kernel.vecquant4matmul(t(x), t(qw), y, t(scales), t(zeros))
+    else:
+        cuda_kernel.vecgroupquant4matmul(t(x), t(qw), y, t(scales), t(zeros), gs)
+    return y.cpu().numpy()
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_golden_known_answers(golden, impl):
+    g = golden("gptq")
+    _lib.load().sb200_gptq4_set_impl(impl)
+    try:
+        for name in g["cases"]:
+            gs = int(g[name + "_gs"])
+            y = _run(g[name + "_x"], g[name + "_qweight"], g[name + "_bias"], g[name + "_scales"], g[name + "_zeros"], gs)
+            np.testing.assert_allclose(y, g[name + "_gt"], err_msg=name, **TOL)
+    finally:
+        _lib.load().sb200_gptq4_set_impl(0)
+
+
+def _make_case(rng, bshape, k, n, gs):
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    scale, zero = ogptq.find_params_int4(w, gs)
+    wq = ogptq.quantize_weight(w, scale, zero, gs)
+    qw, scales, zeros = ogptq.pack_int4(wq, scale, zero)
+    x = rng.standard_normal(bshape + (k,)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32) * 0.1
+    return x, qw, bias, scales, zeros
+
+
+# shapes of test_cuda_kernel.py:50-126 that fit the time budget (irregular sizes, multi-batch, 3-D
+# inputs, GS = 128 / 384), plus the LLaMA-7B linear shapes at decode and prefill-tile M.
+CASES = [
+    ((1,), 128, 64, -1), ((1,), 127, 61, -1), ((1,), 6661, 2516, -1), ((31,), 6661, 2516, -1),
+    ((32, 1), 1024, 1031, -1), ((4, 8), 6661, 512, -1), ((29,), 8192, 1024, 128), ((4,), 6144, 768, 384),
+    ((1,), 4096, 4096, 128), ((1,), 4096, 11008, 128), ((1,), 11008, 4096, 128), ((16,), 4096, 4096, 128),
+    ((256,), 4096, 4096, 128), ((300,), 1024, 512, 128), ((2, 130), 512, 264, 128),
+]
+
+
+@pytest.mark.parametrize("bshape,k,n,gs", CASES)
+def test_vs_fp64_oracle(bshape, k, n, gs):
+    rng = np.random.default_rng(k + n + len(bshape))
+    x, qw, bias, scales, zeros = _make_case(rng, bshape, k, n, gs)
+    y = _run(x, qw, bias, scales, zeros, gs)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, x.shape[:-1] + (n,)), scales, zeros, 0 if gs == -1 else gs)
+    np.testing.assert_allclose(y, exp, **TOL)
+
+
+def test_quant_linear_module_matches_dense_linear():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for (b, k, n, gs) in [(3, 256, 96, -1), (29, 1024, 200, 128)]:
+        layer = torch.nn.Linear(k, n)
+        scale, zero = find_params_int4(layer.weight.data, gs)
+        wq = ogptq.quantize_weight(layer.weight.data.numpy(), scale.reshape(n, -1).numpy(), zero.reshape(n, -1).numpy(), gs)
+        layer.weight.data = torch.from_numpy(wq)
+        ql = QuantLinear(k, n, 4, gs)
+        ql.pack(layer, scale, zero)
+        x = torch.randn(b, k)
+        gt = layer.to(dev())(x.to(dev()))
+        torch.testing.assert_close(ql.to(dev())(x.to(dev())), gt, **TOL)
+        assert ql(x.to(dev()).half()).dtype == torch.float16
+
+
+def test_linearity_and_accumulate_contract_at_llama_shape():
+    """Full L7B down_proj shape, M = 2048: properties instead of a CPU recompute -- the kernel
+    ACCUMULATES into out (bias contract), and is linear in x."""
+    rng = np.random.default_rng(0)
+    k, n, m = 11008, 4096, 2048
+    x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, 128)
+    y1 = _run(x, qw, bias, scales, zeros, 128)
+    y0 = _run(np.zeros_like(x), qw, bias, scales, zeros, 128)
+    np.testing.assert_allclose(y0, np.broadcast_to(bias, (m, n)), rtol=0, atol=1e-6)
+    y2 = _run(2 * x, qw, np.zeros(n, np.float32), scales, zeros, 128)
+    np.testing.assert_allclose(y2, 2 * (y1 - bias), rtol=2e-5, atol=2e-5)
+    rows = [0, 777, 2047]
+    exp = ogptq.dequant_matmul(x[rows], qw, np.broadcast_to(bias, (3, n)), scales, zeros, 128)
+    np.testing.assert_allclose(y1[rows], exp, **TOL)
+
+
+def test_argument_checks():
+    x = torch.randn(4, 256, device=dev())
+    qw = torch.zeros(32, 8, dtype=torch.int32, device=dev())
+    y = torch.zeros(4, 8, device=dev())
+    s = torch.ones(8, 2, device=dev())
+    with pytest.raises(RuntimeError, match="divisible by 128"):
+        cuda_kernel.vecgroupquant4matmul(x, qw, y, s, s, 64)
+    with pytest.raises(RuntimeError, match="dimension >= 2"):
+        cuda_kernel.vecquant4matmul(x[0, :], qw, y[0], s, s)
+    with pytest.raises(RuntimeError, match="out_channel"):
+        cuda_kernel.vecquant4matmul(x, qw, torch.zeros(4, 9, device=dev()), s, s)

@@ -1,0 +1,122 @@
+"""CPU: host-side logic of the plugin mirror -- registries, descriptors, qparams math, the KL
+entropy search, GPTQ packing -- against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gptq as ogptq
+from oracle import observers as oobs
+from sparsebit_b200 import config as sbcfg
+from sparsebit_b200.gptq.quant_linear import QuantLinear, find_params_int4
+from sparsebit_b200.quantization import OBSERVERS_MAP, QUANTIZERS_MAP, build_observer, build_quantizer
+from sparsebit_b200.quantization.common import Backend, get_backend, get_qscheme
+from sparsebit_b200.quantization.observers.kl_histogram import entropy_threshold
+from sparsebit_b200.quantization.quant_descriptor import QuantDescriptor
+from sparsebit_b200.sparse import SPARSERS_MAP, build_sparser
+
+
+def test_registries_hold_reference_type_names():
+    assert "uniform" in QUANTIZERS_MAP
+    assert {"minmax", "mse", "percentile", "kl_histogram"} <= set(OBSERVERS_MAP)
+    assert "l1norm" in SPARSERS_MAP
+    with pytest.raises(AssertionError):  # reference asserts before lower-casing (Q18)
+        build_quantizer(sbcfg.quantizer_config("per-tensor-affine", 8, "feature", qtype="Uniform"))
+    with pytest.raises(TypeError):
+        get_qscheme("per-tensor")
+    assert get_backend("tensorrt") is Backend.TENSORRT
+
+
+@pytest.mark.parametrize(
+    "scheme,bit,target,layout,exp",
+    [
+        ("per-tensor-symmetric", 8, "feature", "NCHW", (-128, 127, 1, 0, False, True)),
+        ("per-tensor-affine", 4, "feature", "NLC", (0, 15, 2, 0, False, False)),
+        ("per-channel-symmetric", 4, "weight", None, (-8, 7, 0, None, True, True)),
+        ("per-channel-affine", 8, "weight", None, (0, 255, 0, None, True, False)),
+    ],
+)
+def test_quant_descriptor(scheme, bit, target, layout, exp):
+    d = QuantDescriptor(sbcfg.quantizer_config(scheme, bit, target, layout=layout or "NCHW"))
+    assert (d.qmin, d.qmax, d.ch_axis, d.bs_axis, d.is_perchannel, d.is_symmetric) == exp
+    assert d.qrange == (d.qmin, d.qmax)
+    d.set_bit(2)
+    assert d.qrange == ((-2, 1) if d.is_symmetric else (0, 3))
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_calc_qparams_with_minmax_matches_oracle(sym):
+    scheme = "per-channel-symmetric" if sym else "per-channel-affine"
+    cfg = sbcfg.quantizer_config(scheme, 8, "weight")
+    obs = build_observer(cfg, QuantDescriptor(cfg))
+    g = torch.Generator().manual_seed(0)
+    mn = -torch.rand(64, generator=g) * 3
+    mx = torch.rand(64, generator=g) * 5
+    mn[:4] = 0.3  # positive minimum -> clamped to 0
+    mx[4:8] = -0.2
+    mn[8], mx[8] = 0.0, 0.0  # degenerate -> scale floor 1e-6
+    s, z = obs.calc_qparams_with_minmax(mn, mx)
+    so, zo = oobs.calc_qparams_with_minmax(mn.numpy(), mx.numpy(), *obs.qdesc.qrange, sym)
+    assert np.array_equal(s.numpy(), so)
+    assert np.array_equal(z.numpy() + 0.0, zo + 0.0)
+
+
+@pytest.mark.parametrize("bit", [8, 4])
+def test_entropy_threshold_matches_reference_restatement(bit):
+    rng = np.random.default_rng(bit)
+    for trial in range(3):
+        x = (rng.standard_normal(20000) * (1 + trial)).astype(np.float32)
+        if trial == 2:
+            x = np.abs(x)
+        am = np.abs(x).max()
+        hist = oobs.histc(x, 2048, -am, am).astype(np.float32)
+        a = oobs.calibrate_entropy(hist, 1.0, 2048, 2**bit - 1)
+        b = entropy_threshold(hist, 1.0, 2048, 2**bit - 1)
+        assert a == b
+    # the documented degenerate behaviour: slot 1025 - 2^bit wins on ordinary data
+    assert b == 1025 - 2**bit
+
+
+def test_gptq_pack_and_find_params_match_reference(golden):
+    g = golden("gptq")
+    for name in g["cases"]:
+        gs = int(g[name + "_gs"])
+        w = torch.from_numpy(g[name + "_wdq"])
+        n, k = w.shape
+        scale, zero = find_params_int4(w, gs)
+        np.testing.assert_array_equal(zero.reshape(n, -1).numpy(), g[name + "_zero_int"])
+        lin = torch.nn.Linear(k, n)
+        lin.weight.data = w
+        lin.bias.data = torch.from_numpy(g[name + "_bias"])
+        ql = QuantLinear(k, n, bit=4, groupsize=gs)
+        ql.pack(lin, scale, zero)
+        np.testing.assert_array_equal(ql.qweight.numpy(), g[name + "_qweight"])
+        np.testing.assert_allclose(ql.scales.reshape(n, -1).numpy(), g[name + "_scales"], rtol=1e-6)
+        np.testing.assert_allclose(ql.zeros.reshape(n, -1).numpy(), g[name + "_zeros"], rtol=1e-6, atol=1e-9)
+        # and the oracle's packer agrees with both
+        qw2, _, _ = ogptq.pack_int4(g[name + "_wdq"], scale.reshape(n, -1).numpy(), zero.reshape(n, -1).numpy())
+        np.testing.assert_array_equal(qw2, g[name + "_qweight"])
+
+
+def test_sparser_builds_and_ratio_zero_is_ones():
+    sp = build_sparser(sbcfg.sparser_config(0.0), opr=None)
+    w = torch.randn(3, 4)
+    assert torch.equal(sp.calc_mask(w), torch.ones_like(w))
+    assert repr(sp) == "unstructed, l1norm, 0.0"
+    sp.set_ratio(0.5)
+    assert sp.ratio == 0.5
+
+
+def test_quantizer_state_contract():
+    q = build_quantizer(sbcfg.quantizer_config("per-channel-symmetric", 8, "weight"))
+    assert set(dict(q.named_buffers())) >= {"scale", "zero_point", "observer.min_val", "observer.max_val"}
+    assert not q.is_enable
+    q.enable_quant()
+    assert q.is_enable
+    q.set_fake_fused()
+    assert not q.is_enable
+    x = torch.randn(4, 4)
+    assert q(x) is x  # disabled quantizer is the identity (base.py:55-64)
+    q.set_backend(Backend.VIRTUAL)
+    assert q.observer.backend is Backend.VIRTUAL
+    q.dims = 4
+    assert q._broadcast_qparams(torch.ones(6)).shape == (6, 1, 1, 1)

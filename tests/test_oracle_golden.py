@@ -98,3 +98,57 @@ def test_gptq_matches_reference(golden):
         qw2, sc2, zr2 = ogptq.pack_int4(g[name + "_wdq"], s2, z2)
         # (dequantised weights re-quantise onto the same grid)
         np.testing.assert_allclose(sc2, s, rtol=1e-6, atol=0)
+
+
+def test_torch_port_matches_reference(golden):
+    """oracle/torch_port.py (the CPU baseline bench.py times) == the reference's outputs."""
+    import torch
+
+    from oracle import torch_port
+
+    g = golden("qdq")
+    for name in g["cases"]:
+        qmin, qmax, ch_axis, perch = (int(v) for v in g[name + "_meta"])
+        x = torch.from_numpy(g[name + "_x"])
+        shape = [1] * x.dim()
+        if perch:
+            shape[ch_axis] = -1
+        s = torch.from_numpy(g[name + "_scale"]).reshape(shape)
+        z = torch.from_numpy(g[name + "_zp"]).reshape(shape)
+        y = torch_port.ort_fake_quant_cpu(x, s, z, qmin, qmax)
+        assert _eq_bits(y.numpy(), g[name + "_y"]), name
+
+
+def test_c_restatement_matches_reference(golden):
+    """oracle/c/libsb_oracle.so (plain C, -ffp-contract=off) == the reference's outputs."""
+    import ctypes
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "c", "libsb_oracle.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/c not built (run __graft_entry__.build())")
+    lib = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    g = golden("qdq")
+    for name in g["cases"]:
+        qmin, qmax, ch_axis, perch = (int(v) for v in g[name + "_meta"])
+        x = np.ascontiguousarray(g[name + "_x"])
+        s, z = np.ascontiguousarray(g[name + "_scale"]), np.ascontiguousarray(g[name + "_zp"])
+        out = np.empty_like(x)
+        if perch:
+            outer = int(np.prod(x.shape[:ch_axis], dtype=np.int64))
+            c, inner = x.shape[ch_axis], int(np.prod(x.shape[ch_axis + 1 :], dtype=np.int64))
+        else:
+            outer, c, inner = 1, 1, x.size
+        lib.sbo_qdq(x.ctypes.data_as(vp), s.ctypes.data_as(vp), z.ctypes.data_as(vp), out.ctypes.data_as(vp),
+                    ctypes.c_int64(outer), ctypes.c_int64(c), ctypes.c_int64(inner), qmin, qmax)
+        assert _eq_bits(out, g[name + "_y"]), name
+    gg = golden("gptq")
+    name = "group128_b29"
+    x, qw = np.ascontiguousarray(gg[name + "_x"]), np.ascontiguousarray(gg[name + "_qweight"])
+    n, k = qw.shape[1], x.shape[-1]
+    out = np.ascontiguousarray(np.broadcast_to(gg[name + "_bias"], (x.shape[0], n))).copy()
+    sc, zr = np.ascontiguousarray(gg[name + "_scales"]), np.ascontiguousarray(gg[name + "_zeros"])
+    lib.sbo_gptq4(x.ctypes.data_as(vp), qw.ctypes.data_as(vp), out.ctypes.data_as(vp), sc.ctypes.data_as(vp),
+                  zr.ctypes.data_as(vp), ctypes.c_int64(x.shape[0]), ctypes.c_int64(k), ctypes.c_int64(n), 128)
+    np.testing.assert_allclose(out, gg[name + "_gt"], rtol=1e-5, atol=1e-5)
