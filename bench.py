@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the fake-quant hot path on B200.
+
+Workload (BASELINE.json configs[1]): the quantize->dequantize work of ONE ResNet-50 QAT forward at
+batch 256, 8w8a: the 55 activation quantizer sites (per-tensor 8-bit, fused QDQ + MinMax-observer
+statistics kernel -- the kernel the 70 %-of-HBM-roofline target is quoted on) and the 54 weight
+quantizer sites (per-channel symmetric 8-bit).  A "step" is one pass over all 109 sites on
+synthetic tensors of exactly those shapes.  metric = fake-quant forward Gelem/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); the path has no exchange step, so ranks are
+independent replicas (weak scaling) and only the timing barrier uses NCCL.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "fake-quant fwd Gelem/s"
+UNIT = "Gelem/s"
+WORKLOAD = ("resnet50_qat_fwd_8w8a_bs256 (BASELINE configs[1]): 55 activation sites per-tensor 8-bit "
+            "fused QDQ+MinMax stats, 54 weight sites per-channel symmetric 8-bit")
+
+
+# ------------------------------------------------------------------------------------------------
+# ResNet-50 quantizer sites (torchvision v1.5 layout: stride on the 3x3), SURVEY.md section 3.2
+def r50_activation_sites(bs):
+    """Input tensor of every QConv2d (53) + QAdaptiveAvgPool2d + QLinear = 55 sites; (shape, post_relu)."""
+    sites = [((bs, 3, 224, 224), False)]
+    inplanes, hw = 64, 56
+    for planes, blocks, stride in [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)]:
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            sites.append(((bs, inplanes, hw, hw), True))            # conv1 1x1
+            sites.append(((bs, planes, hw, hw), True))              # conv2 3x3 (stride s)
+            hw2 = hw // s
+            sites.append(((bs, planes, hw2, hw2), True))            # conv3 1x1
+            if b == 0:
+                sites.append(((bs, inplanes, hw, hw), True))        # downsample 1x1
+            inplanes, hw = planes * 4, hw2
+    sites.append(((bs, 2048, 7, 7), True))                          # avgpool input
+    sites.append(((bs, 2048), False))                               # fc input
+    return sites
+
+
+def r50_weight_sites():
+    ws = [(64, 3, 7, 7)]
+    inplanes = 64
+    for planes, blocks in [(64, 3), (128, 4), (256, 6), (512, 3)]:
+        for b in range(blocks):
+            ws += [(planes, inplanes, 1, 1), (planes, planes, 3, 3), (planes * 4, planes, 1, 1)]
+            if b == 0:
+                ws.append((planes * 4, inplanes, 1, 1))
+            inplanes = planes * 4
+    ws.append((1000, 2048))
+    return ws
+
+
+def numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(acts, weights):
+    """One pass of the reference's CPU op chain (oracle/torch_port.py) over a sample of the workload."""
+    from oracle import torch_port
+
+    for x, s, z in acts:
+        torch_port.ort_fake_quant_cpu(x, s, z, 0, 255)
+        torch_port.minmax_cpu(x)
+    for w, s, z in weights:
+        torch_port.ort_fake_quant_cpu(w, s, z, -128, 127)
+
+
+def build_cpu_sample(sample_bs):
+    g = torch.Generator().manual_seed(0)
+    acts, weights = [], []
+    for shape, relu in r50_activation_sites(sample_bs):
+        x = torch.randn(shape, generator=g)
+        if relu:
+            x = torch.relu(x)
+        s = (x.max() - x.min().clamp(max=0)) / 255.0
+        acts.append((x, s.reshape(1), torch.round(-x.min().clamp(max=0) / s).reshape(1)))
+    for shape in r50_weight_sites():
+        w = torch.randn(shape, generator=g) * (2.0 / numel(shape[1:])) ** 0.5
+        amax = w.reshape(shape[0], -1).abs().max(dim=1).values
+        s = (amax * 2 / 255.0).clamp(min=1e-6).reshape([-1] + [1] * (len(shape) - 1))
+        weights.append((w, s, torch.zeros_like(s)))
+    elems = sum(x.numel() for x, _, _ in acts) + sum(w.numel() for w, _, _ in weights)
+    return acts, weights, elems
+
+
+def time_cpu_baseline(sample_bs, reps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    acts, weights, elems = build_cpu_sample(sample_bs)
+    for _ in range(warmup):
+        cpu_reference_pass(acts, weights)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_pass(acts, weights)
+        times.append(time.perf_counter() - t0)
+    return elems, times
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (torch op chain, all host
+    threads) on a bounded sample of the same workload; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_bs = 32
+    elems, times = time_cpu_baseline(sample_bs, args.steps, args.warmup)
+    total = sum(times)
+    value = elems * len(times) / total / 1e9
+    cores = os.cpu_count() or 1
+    sample = f"all 109 sites at batch {sample_bs} instead of 256 ({elems} elems per step), torch CPU op chain of quant_tensor.py:181-184 + min/max"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": 256 * args.gpus, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [p.strip() for p in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+
+    from sparsebit_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # ---- synthetic workload, resident in HBM -------------------------------------------------
+    bs = 256
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    acts, weights = [], []
+    for shape, relu in r50_activation_sites(bs):
+        x = torch.randn(shape, device=dev, generator=g)
+        if relu:
+            x.relu_()
+        mn, mx = x.min().clamp(max=0), x.max().clamp(min=0)
+        s = ((mx - mn) / 255.0).clamp(min=1e-6).reshape(1)
+        z = torch.round(-mn / s).reshape(1)
+        st = torch.empty(2, dtype=torch.int32, device=dev)
+        acts.append((x, torch.empty_like(x), s, z, st))
+    for shape in r50_weight_sites():
+        w = torch.randn(shape, device=dev, generator=g) * (2.0 / numel(shape[1:])) ** 0.5
+        amax = w.reshape(shape[0], -1).abs().max(dim=1).values
+        s = (amax * 2 / 255.0).clamp(min=1e-6).contiguous()
+        weights.append((w, torch.empty_like(w), s, torch.zeros_like(s)))
+    act_elems = sum(a[0].numel() for a in acts)
+    w_elems = sum(w[0].numel() for w in weights)
+    assert act_elems == 10_764_800 * bs and w_elems == 25_502_912 and len(acts) == 55 and len(weights) == 54
+    step_elems = act_elems + w_elems
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    act_calls = [(a[0].data_ptr(), a[2].data_ptr(), a[3].data_ptr(), a[1].data_ptr(), a[4].data_ptr(), a[0].numel(), 0, 255, 0, stream)
+                 for a in acts]
+    init_calls = [(a[4].data_ptr(), 1, stream) for a in acts]
+    w_calls = [(w[0].data_ptr(), w[2].data_ptr(), w[3].data_ptr(), w[1].data_ptr(), 1, w[0].shape[0], numel(w[0].shape[1:]), -128, 127, 0, stream)
+               for w in weights]
+    ev_a0 = torch.cuda.Event(enable_timing=True)
+    ev_a1 = torch.cuda.Event(enable_timing=True)
+
+    def step(mark=False):
+        for c in init_calls:
+            lib.sb200_minmax_init(*c)
+        if mark:
+            ev_a0.record()
+        for c in act_calls:
+            rc = lib.sb200_qdq_stats_pertensor_fwd(*c)
+            if rc:
+                _lib.check(rc, "qdq_stats")
+        if mark:
+            ev_a1.record()
+        for c in w_calls:
+            rc = lib.sb200_qdq_perchannel_fwd(*c)
+            if rc:
+                _lib.check(rc, "qdq_perchannel")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    act_ms = 0.0
+    ev0.record()
+    pending = []
+    for _ in range(args.steps):
+        step(mark=True)
+        # event pairs are read after the loop; re-recording the same pair would lose timings, so
+        # collect this step's activation-group time lazily with fresh events every step
+        pending.append((ev_a0, ev_a1))
+        ev_a0 = torch.cuda.Event(enable_timing=True)
+        ev_a1 = torch.cuda.Event(enable_timing=True)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev0.elapsed_time(ev1)
+    act_ms = sum(a.elapsed_time(b) for a, b in pending)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax)
+    ms_per_step = total_ms / args.steps
+    value = world * step_elems / (ms_per_step * 1e-3) / 1e9
+
+    # parity spot check of what was just timed (fused kernel's min/max state, on-grid outputs)
+    mn, mx = (torch.empty(1, device=dev), torch.empty(1, device=dev))
+    lib.sb200_minmax_read(acts[0][4].data_ptr(), 1, mn.data_ptr(), mx.data_ptr(), stream)
+    assert float(mn) == float(acts[0][0].min()) and float(mx) == float(acts[0][0].max()), "fused stats mismatch"
+
+    # ---- roofline of the dominant kernel (fused QDQ + stats), measured inside the timed region --
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    act_launches = 55 * args.steps
+    alg_bytes_per_launch = act_elems * 8.0 / 55
+    avg_launch_s = act_ms * 1e-3 / act_launches
+    achieved = alg_bytes_per_launch / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "sb200::stream_kernel<MODE_TENSOR,VEC4,DOQ,STORE,STATS> (sb200_qdq_stats_pertensor_fwd)",
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
+                "kernel_share_of_step": act_ms / (ms_per_step * args.steps), "peak_source": peak_src}
+    # headline tensor alone: [256,3,224,224] (308 MB in+out > L2), 30 back-to-back launches
+    a0 = act_calls[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(5):
+        lib.sb200_qdq_stats_pertensor_fwd(*a0)
+    e0.record()
+    for _ in range(30):
+        lib.sb200_qdq_stats_pertensor_fwd(*a0)
+    e1.record()
+    torch.cuda.synchronize()
+    a0_us = e0.elapsed_time(e1) * 1e3 / 30
+    a0_gbs = acts[0][0].numel() * 8.0 / (a0_us * 1e-6) / 1e9
+    roofline["headline_256x3x224x224"] = {"us": a0_us, "GB/s": a0_gbs, "frac": a0_gbs / peak, "Gelem/s": acts[0][0].numel() / (a0_us * 1e-6) / 1e9}
+
+    # ---- end to end: host buffers through the C-ABI host entry points ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        max_a = max(a[0].numel() for a in acts)
+        max_w = max(w[0].numel() for w in weights)
+        hx = torch.empty(max_a, dtype=torch.float32).pin_memory()
+        hy = torch.empty(max_a, dtype=torch.float32).pin_memory()
+        hx.copy_(torch.relu(torch.randn(max_a, generator=torch.Generator().manual_seed(7))))
+        hw = torch.randn(max_w).pin_memory()
+        hwy = torch.empty(max_w).pin_memory()
+        hs = torch.full((2048,), 0.01)
+        hz = torch.zeros(2048)
+        mm = (ctypes.c_float * 2)()
+        a_host = [(hx.data_ptr(), ctypes.c_float(float(a[2])), ctypes.c_float(float(a[3])), hy.data_ptr(), ctypes.addressof(mm),
+                   a[0].numel(), 0, 255, 0) for a in acts]
+        w_host = [(hw.data_ptr(), hs.data_ptr(), hz.data_ptr(), hwy.data_ptr(), 1, w[0].shape[0], numel(w[0].shape[1:]), -128, 127, 0)
+                  for w in weights]
+
+        def e2e_step():
+            for c in a_host:
+                rc = lib.sb200_qdq_pertensor_fwd_host(*c)
+                if rc:
+                    _lib.check(rc, "qdq_host")
+            for c in w_host:
+                rc = lib.sb200_qdq_perchannel_fwd_host(*c)
+                if rc:
+                    _lib.check(rc, "qdq_pc_host")
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * step_elems * e2e_steps / float(dt) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": step_elems * 4 + 2 * 4 * sum(w[0].shape[0] for w in weights),
+               "d2h_bytes_per_step": step_elems * 4 + 8 * len(acts), "steps": e2e_steps,
+               "api": "sb200_qdq_pertensor_fwd_host (+minmax) / sb200_qdq_perchannel_fwd_host, pinned host buffers, H2D+D2H inside"}
+        del hx, hy, hw, hwy
+
+    # ---- CPU baseline: the reference's CPU op chain on this box's host cores --------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample_bs = 32
+        elems, times = time_cpu_baseline(sample_bs, reps=3, warmup=1)
+        cpu = {"value": elems * len(times) / sum(times) / 1e9, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"all 109 sites at batch {sample_bs} instead of 256 ({elems} elems per pass, {len(times)} passes), torch CPU "
+                         "op chain of quant_tensor.py:181-184 + min/max (oracle/torch_port.py)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": bs * world, "act_elems_per_gpu": act_elems, "weight_elems_per_gpu": w_elems,
+                       "parallelism": f"replicas x{world} (path has no exchange step; no data-path collective)",
+                       "l2": "inputs larger than L2: 22 GB working set per step, every site owns its in/out buffers"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -129,12 +129,15 @@ class Observer(nn.Module):
         max_pos = torch.maximum(max_val, zero)
         qmin, qmax = self.qdesc.qrange
         floor = torch.tensor(1e-6, device=min_neg.device)
+        # tensor / tensor: torch-CUDA turns "tensor / python_scalar" into a multiply by the
+        # reciprocal (1 ulp off the CPU result the oracle pins); a tensor divisor is a true division
+        span = torch.tensor(float(qmax - qmin), dtype=torch.float32, device=min_neg.device)
         if self.is_symmetric:
             bound = torch.maximum(-min_neg, max_pos)
-            scale = torch.maximum(bound * 2 / float(qmax - qmin), floor)
+            scale = torch.maximum(bound * 2 / span, floor)
             zero_point = torch.zeros(min_neg.size(), dtype=torch.float32, device=min_neg.device)
         else:
-            scale = torch.maximum((max_pos - min_neg) / float(qmax - qmin), floor)
+            scale = torch.maximum((max_pos - min_neg) / span, floor)
             zero_point = torch.round(-min_neg / scale)
         assert len(self.data_cache) == 0, "free data cache after calc_qparams"
         return scale, zero_point
