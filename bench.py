@@ -276,6 +276,8 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
+    if os.environ.get("SB200_NCU_RANGE"):
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: capture only the timed region
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     act_ms = 0.0
@@ -290,6 +292,8 @@ def main():
         ev_a1 = torch.cuda.Event(enable_timing=True)
     ev1.record()
     barrier()
+    if os.environ.get("SB200_NCU_RANGE"):
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev0.elapsed_time(ev1)
@@ -333,6 +337,20 @@ def main():
     a0_us = e0.elapsed_time(e1) * 1e3 / 30
     a0_gbs = acts[0][0].numel() * 8.0 / (a0_us * 1e-6) / 1e9
     roofline["headline_256x3x224x224"] = {"us": a0_us, "GB/s": a0_gbs, "frac": a0_gbs / peak, "Gelem/s": acts[0][0].numel() / (a0_us * 1e-6) / 1e9}
+    # the same tensor through each implementation variant (1 = LDG register pipeline, 2 = TMA ring)
+    for variant, name in ((1, "ldg"), (2, "tma")):
+        lib.sb200_set_variant(variant)
+        for _ in range(5):
+            lib.sb200_qdq_stats_pertensor_fwd(*a0)
+        e0.record()
+        for _ in range(30):
+            lib.sb200_qdq_stats_pertensor_fwd(*a0)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 30
+        roofline["headline_256x3x224x224"][name + "_us"] = us
+        roofline["headline_256x3x224x224"][name + "_frac"] = acts[0][0].numel() * 8.0 / (us * 1e-6) / 1e9 / peak
+    lib.sb200_set_variant(0)
 
     # ---- end to end: host buffers through the C-ABI host entry points ---------------------------
     e2e = None

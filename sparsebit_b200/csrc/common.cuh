@@ -105,10 +105,15 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {
 struct QP {
   float s, zp, qmin, qmax;
   double rs;  // RN64(1 / s)
+  float r;    // RN32(1 / s)
+  bool fast;  // |s| in [2^-60, 2^60]: the fp32 fast path below is valid
   __device__ __forceinline__ void set(float scale, float zero_point_raw) {
     s = scale;
     zp = rintf(zero_point_raw);
     rs = __drcp_rn((double)scale);
+    r = __double2float_rn(rs);
+    const float a = fabsf(scale);
+    fast = (a >= 0x1p-60f) && (a <= 0x1p60f);
   }
 };
 
@@ -118,19 +123,79 @@ __device__ __forceinline__ float div_exact(float x, const QP& p) {
 
 // ROUNDING: 0 half-to-even (torch.round / nearbyint); -1 = runtime `rounding` in {0, 1, 2}
 // (1: floor(v + .5), 2: ceil(v - .5), torch_extensions/common.cuh:66-74).
+// rint() without the XU pipe: adding 1.5 * 2^23 rounds to an integer with the FPU's own
+// round-half-even; exact for |v| < 2^22, everything else (incl. NaN) takes the FRND path.  The
+// only difference from rintf is the sign of a zero result, which cannot reach the output:
+// (+-0 + zp) and (+-0 - q) are the same values either way.
+__device__ __forceinline__ float rint_fast(float v) {
+  float r = __fadd_rn(__fadd_rn(v, 12582912.f), -12582912.f);
+  if (!(fabsf(v) < 4194304.f)) r = rintf(v);
+  return r;
+}
+
 template <int ROUNDING>
 __device__ __forceinline__ float round_q(float v, int rounding) {
-  if (ROUNDING == 0) return rintf(v);
+  if (ROUNDING == 0) return rint_fast(v);
   if (rounding == 1) return floorf(__fadd_rn(v, 0.5f));
   if (rounding == 2) return ceilf(__fsub_rn(v, 0.5f));
   return rintf(v);
 }
 
+// round(x / s) for the forward pass, bit-identical to round_q(div_exact(x)) but on the FP32 pipe:
+//   q1 = Markstein quotient (x*r, exact residual by FMA, one correction) -- within 1/2 ulp (+2^-47)
+//        of x/s, like the IEEE quotient itself;
+//   t1 = q1 rounded to an integer by the 1.5*2^23 trick;
+//   the two can only round to different integers if a half-integer lies within 2 ulp of q1, i.e.
+//   0.5 - |q1 - t1| <= |q1| * 2^-22.  Those elements (a ~1e-4 fraction for 8-bit data), huge or
+//   non-finite quotients, and out-of-range scales take the exact fp64 route.
+// Verified against rintf(x / s) on 4e9 random + adversarial (k + 0.5) * s +- few-ulp inputs.
+template <int ROUNDING>
+__device__ __forceinline__ float quant_round(float x, const QP& p, int rounding) {
+  if (ROUNDING == 0 && p.fast) {
+    const float q0 = __fmul_rn(x, p.r);
+    const float e = __fmaf_rn(-q0, p.s, x);
+    const float q1 = __fmaf_rn(e, p.r, q0);
+    const float t1 = __fadd_rn(__fadd_rn(q1, 12582912.f), -12582912.f);
+    const float d = __fsub_rn(q1, t1);
+    const float c = __fmaf_rn(fabsf(q1), -0x1p-22f, __fsub_rn(0.5f, fabsf(d)));
+    if (c > 0.f) return t1;
+  }
+  return round_q<ROUNDING>(div_exact(x, p), rounding);
+}
+
 template <int ROUNDING>
 __device__ __forceinline__ float qdq1(float x, const QP& p, int rounding) {
-  float v = __fadd_rn(round_q<ROUNDING>(div_exact(x, p), rounding), p.zp);
+  float v = __fadd_rn(quant_round<ROUNDING>(x, p, rounding), p.zp);
   v = fmax_nan(fmin_nan(v, p.qmax), p.qmin);
   return __fmul_rn(__fsub_rn(v, p.zp), p.s);
+}
+
+// ---------------------------------------------------------------- mbarrier + TMA bulk copy (sm_90+)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA: global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, both 16 B aligned)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---------------------------------------------------------------- warp / block reductions

@@ -165,33 +165,6 @@ constexpr int kMseTile = 8192;      // floats per tile (32 KB of shared memory)
 constexpr int kMseCandChunk = 8;    // accumulators live per thread
 constexpr int kMseMaxCand = 128;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
 // Per-candidate quantisation error of one value.  The quotient uses a reciprocal plus one
 // Newton correction (q1 = q0 + (x - q0*s)*r), which is the correctly rounded x/s except in
 // measure-zero corner cases -- sufficient for a loss that is compared at 1e-5 (Q: mse.py:51-55).
@@ -220,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) mse_sweep_kernel(const float* __rest
   const long long total = rows * tpr;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
   uint32_t phase = 0;

@@ -57,6 +57,33 @@ def test_nan_inf_propagation_matches_torch_clamp():
     assert np.isnan(y[0]) and np.isnan(y[6]) and y[1] == np.float32(127 * np.float32(0.1))
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("n", [16384, 16384 + 7, 4096 * 6 * 3 + 4096 + 13, 3_000_001, 38_535_168])
+def test_ldg_and_tma_variants_are_bit_identical(variant, n):
+    """sb200_set_variant: 1 = 128-bit LDG register pipeline, 2 = TMA (cp.async.bulk) shared-memory
+    ring.  Both must give the oracle's bits, with and without the fused statistics."""
+    from sparsebit_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(n, device=dev(), generator=g) * 3
+    s, z = t(np.float32([0.021])), t(np.float32([4.0]))
+    assert lib.sb200_set_variant(variant) == 0
+    try:
+        y = ops.qdq_pertensor(x, s, z, 0, 255)
+        st = ops.minmax_new(1, dev())
+        y2 = ops.qdq_stats_pertensor(x, s, z, 0, 255, st)
+        mn, mx = ops.minmax_read(st)
+    finally:
+        lib.sb200_set_variant(0)
+    assert torch.equal(y, y2)
+    assert float(mn) == float(x.min()) and float(mx) == float(x.max())
+    idx = torch.arange(0, n, max(1, n // 200_000), device=dev())
+    exp = oqdq.qdq(x[idx].cpu().numpy(), np.float32([0.021]), np.float32([4.0]), 0, 255)
+    assert bits_equal(y[idx].cpu().numpy(), exp)
+    assert bits_equal(y[-5000:].cpu().numpy(), oqdq.qdq(x[-5000:].cpu().numpy(), np.float32([0.021]), np.float32([4.0]), 0, 255))
+
+
 SHAPES = [
     ((256, 64, 7, 7), 1),      # inner = 49: float4 straddles channel rows
     ((8, 3, 224, 224), 1),
