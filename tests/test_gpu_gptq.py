@@ -65,6 +65,47 @@ def test_vs_fp64_oracle(bshape, k, n, gs):
     np.testing.assert_allclose(y, exp, **TOL)
 
 
+# tcgen05 path forced (sb200_gptq4_set_impl(2)): ragged M / N tiles, odd number of 64-K stages,
+# group sizes 128 / 256 / 384, a single row, outlier activations (per-row power-of-two scaling).
+TC_CASES = [
+    ((1,), 128, 128, 128), ((128,), 256, 128, 128), ((130,), 512, 264, 128), ((29,), 8192, 1024, 128),
+    ((4,), 6144, 768, 384), ((300,), 1024, 512, 256), ((2, 130), 512, 260, 128), ((257,), 192 * 2, 132, 128),
+    ((256,), 4096, 4096, 128), ((64,), 11008, 512, 128),
+]
+
+
+@pytest.mark.parametrize("bshape,k,n,gs", TC_CASES)
+def test_tcgen05_path_vs_fp64_oracle(bshape, k, n, gs):
+    rng = np.random.default_rng(7 * k + n + len(bshape))
+    x, qw, bias, scales, zeros = _make_case(rng, bshape, k, n, gs)
+    xf = x.reshape(-1, k)
+    xf[0, :5] = [3e4, -7e4, 1e-6, 0.0, 123.0]  # fp16-overflowing magnitudes are fine after row scaling
+    if xf.shape[0] > 2:
+        xf[2] *= 1e-4
+    lib = _lib.load()
+    assert lib.sb200_gptq4_set_impl(2) == 0
+    try:
+        y = _run(x, qw, bias, scales, zeros, gs)
+    finally:
+        lib.sb200_gptq4_set_impl(0)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, x.shape[:-1] + (n,)), scales, zeros, gs)
+    # same tolerance form as the reference's test, relative to each row's magnitude
+    rowmag = np.maximum(np.abs(exp).max(axis=-1, keepdims=True), 1.0)
+    np.testing.assert_array_less(np.abs(y - exp), 1e-5 + 1e-5 * rowmag * np.ones_like(exp))
+
+
+def test_tcgen05_forced_on_unsupported_shape_is_an_error():
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    x, qw, bias, scales, zeros = _make_case(rng, (4,), 127, 61, -1)
+    lib.sb200_gptq4_set_impl(2)
+    try:
+        with pytest.raises(RuntimeError, match="unsupported"):
+            _run(x, qw, bias, scales, zeros, -1)
+    finally:
+        lib.sb200_gptq4_set_impl(0)
+
+
 def test_quant_linear_module_matches_dense_linear():
     torch.backends.cuda.matmul.allow_tf32 = False
     for (b, k, n, gs) in [(3, 256, 96, -1), (29, 1024, 200, 128)]:
