@@ -105,8 +105,38 @@ def build_cpu_sample(sample_bs):
     return acts, weights, elems
 
 
-def time_cpu_baseline(sample_bs, reps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def pick_cpu_setup(budget_s):
+    """Choose the thread count (all usable host threads, or fewer if that is faster -- oversubscribed
+    elementwise ATen ops collapse on some hosts) and the sample batch size so that one pass of the
+    reference's CPU op chain takes about `budget_s` seconds."""
+    probe_acts, probe_w, probe_elems = build_cpu_sample(1)
+    best = None
+    n = host_threads()
+    for threads in sorted({n, min(n, 64), min(n, 32), min(n, 16), min(n, 8)}, reverse=True):
+        torch.set_num_threads(threads)
+        cpu_reference_pass(probe_acts, probe_w)
+        t0 = time.perf_counter()
+        cpu_reference_pass(probe_acts, probe_w)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (threads, dt)
+    threads, dt = best
+    torch.set_num_threads(threads)
+    rate = probe_elems / dt
+    per_image = 10_764_800
+    bs = int(max(1, min(32, (rate * budget_s - 25_502_912) // per_image)))
+    return threads, bs
+
+
+def time_cpu_baseline(reps, warmup, budget_s=1.0):
+    threads, sample_bs = pick_cpu_setup(budget_s)
     acts, weights, elems = build_cpu_sample(sample_bs)
     for _ in range(warmup):
         cpu_reference_pass(acts, weights)
@@ -115,27 +145,28 @@ def time_cpu_baseline(sample_bs, reps, warmup):
         t0 = time.perf_counter()
         cpu_reference_pass(acts, weights)
         times.append(time.perf_counter() - t0)
-    return elems, times
+    return elems, times, threads, sample_bs
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path (torch op chain, all host
-    threads) on a bounded sample of the same workload; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (torch op chain of
+    quant_tensor.py:181-184 + min/max, all usable host threads) on a bounded sample of the same
+    workload; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_bs = 32
-    elems, times = time_cpu_baseline(sample_bs, args.steps, args.warmup)
+    os.environ.pop("OMP_NUM_THREADS", None)  # torchrun pins it to 1
+    elems, times, threads, sample_bs = time_cpu_baseline(args.steps, args.warmup, budget_s=1.5)
     total = sum(times)
     value = elems * len(times) / total / 1e9
-    cores = os.cpu_count() or 1
-    sample = f"all 109 sites at batch {sample_bs} instead of 256 ({elems} elems per step), torch CPU op chain of quant_tensor.py:181-184 + min/max"
+    sample = (f"all 109 sites at batch {sample_bs} instead of 256 ({elems} elems per step), torch CPU op chain of "
+              "quant_tensor.py:181-184 + min/max (oracle/torch_port.py)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": 256 * args.gpus, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -399,9 +430,8 @@ def main():
     # ---- CPU baseline: the reference's CPU op chain on this box's host cores --------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample_bs = 32
-        elems, times = time_cpu_baseline(sample_bs, reps=3, warmup=1)
-        cpu = {"value": elems * len(times) / sum(times) / 1e9, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        elems, times, threads, sample_bs = time_cpu_baseline(reps=5, warmup=1, budget_s=2.0)
+        cpu = {"value": elems * len(times) / sum(times) / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"all 109 sites at batch {sample_bs} instead of 256 ({elems} elems per pass, {len(times)} passes), torch CPU "
                          "op chain of quant_tensor.py:181-184 + min/max (oracle/torch_port.py)"}
 

@@ -1,0 +1,99 @@
+"""GPTQ int4 g128 on the LLaMA-7B linear shapes: this repo (SIMT decode path, tcgen05 prefill path)
+vs the REFERENCE's own CUDA kernel built from /root/reference into oracle/_ref/gptq_ref.so
+(oracle/build_ref.py).  Benchmark infrastructure; prints one JSON line per (shape, M, impl).
+
+Timing: CUDA events, >= 3 warm-ups, rotating over enough distinct weight copies that the packed
+weights of consecutive launches exceed L2 (126 MB) at decode sizes.
+"""
+import importlib.util
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from sparsebit_b200 import _lib, ops
+
+dev = torch.device("cuda:0")
+SHAPES = [("qkvo", 4096, 4096, 4), ("gate_up", 4096, 11008, 2), ("down", 11008, 4096, 1)]  # name, K, N, count per layer
+LAYERS = 32
+
+
+def load_ref():
+    path = os.path.join(ROOT, "oracle", "_ref", "gptq_ref.so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("gptq_ref", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make(k, n, copies, gs=128):
+    g = torch.Generator(device=dev).manual_seed(k + n)
+    out = []
+    for _ in range(copies):
+        qw = torch.randint(-2**31, 2**31 - 1, (k // 8, n), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+        scales = torch.rand(n, k // gs, device=dev, generator=g) * 0.01 + 0.002
+        zeros = scales * torch.randint(0, 16, (n, k // gs), device=dev, generator=g).float()
+        out.append((qw, scales.contiguous(), zeros.contiguous()))
+    return out
+
+
+def timeit(fn, reps):
+    for _ in range(3):
+        fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def main():
+    ref = load_ref()
+    lib = _lib.load()
+    ms = [int(a) for a in sys.argv[1:]] or [1, 16, 2048]
+    totals = {}
+    for m in ms:
+        for name, k, n, cnt in SHAPES:
+            wbytes = k * n // 2
+            copies = max(2, min(24, (256 << 20) // wbytes + 1)) if m <= 64 else 2
+            ws = make(k, n, copies)
+            x = torch.randn(m, k, device=dev)
+            y = torch.zeros(m, n, device=dev)
+            impls = [("ours_auto", 0)] + ([("ours_simt", 1)] if m <= 64 else []) + [("ours_tcgen05", 2)]
+            for label, impl in impls:
+                lib.sb200_gptq4_set_impl(impl)
+                try:
+                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128), 20 if m > 64 else 50)
+                except RuntimeError as e:
+                    print(json.dumps({"shape": name, "M": m, "impl": label, "error": str(e)[:100]}))
+                    continue
+                finally:
+                    lib.sb200_gptq4_set_impl(0)
+                rec = {"shape": name, "K": k, "N": n, "M": m, "impl": label, "us": t * 1e6, "TFLOPs": 2.0 * m * k * n / t / 1e12,
+                       "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9}
+                print(json.dumps(rec))
+                totals.setdefault((m, label), 0.0)
+                totals[(m, label)] += t * cnt * LAYERS
+            if ref is not None:
+                reps = 3 if m > 64 else 50
+                t = timeit(lambda i: ref.vecgroupquant4matmul(x, ws[i % copies][0], y, ws[i % copies][1], ws[i % copies][2], 128), reps)
+                print(json.dumps({"shape": name, "K": k, "N": n, "M": m, "impl": "reference_cuda", "us": t * 1e6,
+                                  "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9}))
+                totals.setdefault((m, "reference_cuda"), 0.0)
+                totals[(m, "reference_cuda")] += t * cnt * LAYERS
+            del ws
+    for (m, label), t in sorted(totals.items()):
+        print(json.dumps({"summary": "llama7b_all_linears", "M": m, "impl": label, "ms_per_forward": t * 1e3, "tok_per_s": m / t}))
+
+
+if __name__ == "__main__":
+    main()
