@@ -1,0 +1,73 @@
+"""Turn ncu artefacts in gpurun_out/ into the small text summaries committed under profiles/.
+usage: python scripts/summarize_ncu.py <tag>"""
+import collections
+import csv
+import subprocess
+import sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+
+def launch_list():
+    rows = [r for r in csv.reader(open(f"gpurun_out/launches_{tag}.csv")) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        k = r[ki].split("(")[0][:90]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    out = [f"# ncu launch list of bench.py's timed region ({tag}): `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none`",
+           "# (per-launch times are cold-cache and serialised: compare SHARES, not absolutes)", "",
+           f"{'launches':>8} {'total_us':>12} {'share':>7}  kernel"]
+    for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out.append(f"{n:8d} {t / 1e3:12.1f} {100 * t / tot:6.1f}%  {k}")
+    out.append(f"{sum(v[0] for v in agg.values()):8d} {tot / 1e3:12.1f}  100.0%  TOTAL")
+    return "\n".join(out)
+
+
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+           "dram__bytes_write.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+           "dram__cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+           "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+           "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+           "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+
+
+def report(name):
+    raw = subprocess.run(["ncu", "-i", f"gpurun_out/{name}_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return f"# {name}: no data"
+    hdr, units = rows[0], rows[1]
+    out = [f"# ncu --set full --clock-control none, report gpurun_out/{name}_{tag}.ncu-rep (summary of selected raw metrics)"]
+    tens = [h for h in hdr if "tensor" in h and "pct_of_peak_sustained_active" in h and ".avg" in h]
+    for r in rows[2:]:
+        out.append("")
+        out.append("kernel: " + r[hdr.index("Kernel Name")][:150])
+        for m in METRICS + [t for t in tens if t not in METRICS]:
+            if m in hdr:
+                out.append(f"  {m:88s} {r[hdr.index(m)]:>18s} {units[hdr.index(m)]}")
+    return "\n".join(out)
+
+
+open(f"profiles/{tag}_bench_launch_list.txt", "w").write(launch_list() + "\n")
+for name in ["prof_qdq_stats", "prof_gptq_tc", "prof_gptq_simt"]:
+    try:
+        open(f"profiles/{tag}_{name}.txt", "w").write(report(name) + "\n")
+    except Exception as e:
+        print("skip", name, e)
+print(open(f"profiles/{tag}_bench_launch_list.txt").read())
