@@ -43,17 +43,28 @@ def make(k, n, copies, gs=128):
     return out
 
 
-def timeit(fn, reps):
-    for _ in range(3):
-        fn(0)
+def timeit(fn, reps, copies=1):
+    """GPU time per launch: `copies` launches (one per rotating weight copy) are captured into a CUDA
+    graph and the graph is replayed -- decode-sized kernels are shorter than a Python launch."""
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for i in range(min(copies, 3)):
+            fn(i)
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for i in range(copies):
+                fn(i)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nrep = max(1, reps // copies)
     e0.record()
-    for i in range(reps):
-        fn(i)
+    for _ in range(nrep):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / reps
+    return e0.elapsed_time(e1) * 1e-3 / (nrep * copies)
 
 
 def main():
@@ -72,7 +83,7 @@ def main():
             for label, impl in impls:
                 lib.sb200_gptq4_set_impl(impl)
                 try:
-                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128), 20 if m > 64 else 50)
+                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128), 20 if m > 64 else 200, copies)
                 except RuntimeError as e:
                     print(json.dumps({"shape": name, "M": m, "impl": label, "error": str(e)[:100]}))
                     continue
@@ -84,8 +95,8 @@ def main():
                 totals.setdefault((m, label), 0.0)
                 totals[(m, label)] += t * cnt * LAYERS
             if ref is not None:
-                reps = 3 if m > 64 else 50
-                t = timeit(lambda i: ref.vecgroupquant4matmul(x, ws[i % copies][0], y, ws[i % copies][1], ws[i % copies][2], 128), reps)
+                reps = 4 if m > 64 else 200
+                t = timeit(lambda i: ref.vecgroupquant4matmul(x, ws[i % copies][0], y, ws[i % copies][1], ws[i % copies][2], 128), reps, copies)
                 print(json.dumps({"shape": name, "K": k, "N": n, "M": m, "impl": "reference_cuda", "us": t * 1e6,
                                   "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9}))
                 totals.setdefault((m, "reference_cuda"), 0.0)
