@@ -78,6 +78,9 @@ def main():
             copies = max(2, min(24, (256 << 20) // wbytes + 1)) if m <= 64 else 2
             ws = make(k, n, copies)
             x = torch.randn(m, k, device=dev)
+            if os.environ.get("SB200_FP16_ACTS", "1") == "1":
+                # the reference's model path: fp16 activations cast to fp32 (utils/quant.py:262-277)
+                x = x.half().float()
             y = torch.zeros(m, n, device=dev)
             impls = [("ours_auto", 0)] + ([("ours_simt", 1)] if m <= 64 else []) + [("ours_tcgen05", 2)]
             for label, impl in impls:
@@ -89,7 +92,7 @@ def main():
                     continue
                 finally:
                     lib.sb200_gptq4_set_impl(0)
-                rec = {"shape": name, "K": k, "N": n, "M": m, "impl": label, "us": t * 1e6, "TFLOPs": 2.0 * m * k * n / t / 1e12,
+                rec = {"shape": name, "K": k, "N": n, "M": m, "impl": label, "acts": "fp16->fp32" if os.environ.get("SB200_FP16_ACTS", "1") == "1" else "fp32", "us": t * 1e6, "TFLOPs": 2.0 * m * k * n / t / 1e12,
                        "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9}
                 print(json.dumps(rec))
                 totals.setdefault((m, label), 0.0)

@@ -142,58 +142,123 @@ __global__ void __launch_bounds__(kThreads) bwd_rows_kernel(const float* __restr
   }
 }
 
-// Stage 2 for row tiles: channel c sums partial[(o*C + c)*tpr + j] over o, j (one warp per channel).
+// Stage 2 for row tiles: channel c sums partial[(o*C + c)*tpr + j] over o, j.  One CTA per channel,
+// fixed thread -> item mapping and a fixed-order tree, so the result is deterministic.
 __global__ void __launch_bounds__(kThreads) bwd_rows_finish_kernel(const double2* __restrict__ partial, long long outer,
                                                                    int channels, long long tpr,
                                                                    float* __restrict__ gs, float* __restrict__ gzp) {
-  const int lane = threadIdx.x & 31;
-  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= channels) return;
+  __shared__ double s_red[2][kThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long c = blockIdx.x;
   const long long cnt = outer * tpr;
   double t0 = 0.0, t1 = 0.0;
-  for (long long i = lane; i < cnt; i += 32) {
-    const long long o = i / tpr, j = i - o * tpr;
-    const double2 v = partial[(o * channels + c) * tpr + j];
-    t0 += v.x;
-    t1 += v.y;
+  if (tpr == 1) {
+    for (long long o = threadIdx.x; o < outer; o += kThreads) {
+      const double2 v = partial[o * channels + c];
+      t0 += v.x;
+      t1 += v.y;
+    }
+  } else {
+    for (long long i = threadIdx.x; i < cnt; i += kThreads) {
+      const long long o = i / tpr, j = i - o * tpr;
+      const double2 v = partial[(o * channels + c) * tpr + j];
+      t0 += v.x;
+      t1 += v.y;
+    }
   }
   t0 = warp_sum(t0);
   t1 = warp_sum(t1);
   if (lane == 0) {
-    if (gs) gs[c] = (float)t0;
-    if (gzp) gzp[c] = (float)t1;
+    s_red[0][wid] = t0;
+    s_red[1][wid] = t1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      a0 += s_red[0][w];
+      a1 += s_red[1][w];
+    }
+    if (gs) gs[c] = (float)a0;
+    if (gzp) gzp[c] = (float)a1;
   }
 }
 
-// Channel-last ([R, C], inner == 1): thread owns one channel, walks a block of rows.
-template <int ROUNDING>
+// Channel-last ([R, C], inner == 1): a thread owns VEC adjacent channels (128-bit loads of x, gy and
+// stores of gx, adjacent threads -> adjacent 16-byte columns) and walks a block of rows two at a time.
+template <int VEC, int ROUNDING>
 __global__ void __launch_bounds__(128) bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ gy,
                                                        float* __restrict__ gx, const float* __restrict__ scale,
                                                        const float* __restrict__ zero_point, long long R, int channels,
                                                        long long rows_per_block, float qmin, float qmax, int rounding,
                                                        double2* __restrict__ partial) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= channels) return;
-  QP p;
-  p.set(__ldg(scale + c), __ldg(zero_point + c));
-  p.qmin = qmin;
-  p.qmax = qmax;
-  const float lo_term = __fsub_rn(p.qmin, p.zp), hi_term = __fsub_rn(p.qmax, p.zp);
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = channels / VEC;
+  if (q >= nq) return;
+  QP p[VEC];
+  float lo_term[VEC], hi_term[VEC];
+  BwdAcc a[VEC];
+  double d0[VEC], d1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    p[j].set(__ldg(scale + q * VEC + j), __ldg(zero_point + q * VEC + j));
+    p[j].qmin = qmin;
+    p[j].qmax = qmax;
+    lo_term[j] = __fsub_rn(qmin, p[j].zp);
+    hi_term[j] = __fsub_rn(qmax, p[j].zp);
+    a[j].gs = a[j].gzp = 0.f;
+    d0[j] = d1[j] = 0.0;
+  }
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
-  BwdAcc a = {0.f, 0.f};
-  double d0 = 0.0, d1 = 0.0;
   int k = 0;
-  for (long long r = r0; r < r1; ++r) {
-    const long long e = r * channels + c;
-    gx[e] = bwd1<ROUNDING>(__ldcs(x + e), __ldcs(gy + e), p, lo_term, hi_term, a, rounding);
-    if (++k == 256) {  // bound fp32 accumulation length
-      d0 += a.gs; d1 += a.gzp; a.gs = 0.f; a.gzp = 0.f; k = 0;
+  if (VEC == 4) {
+    const float4* x4 = reinterpret_cast<const float4*>(x) + q;
+    const float4* g4 = reinterpret_cast<const float4*>(gy) + q;
+    float4* o4 = reinterpret_cast<float4*>(gx) + q;
+    long long r = r0;
+    for (; r + 1 < r1; r += 2) {
+      const float4 xa = ld_stream4(x4 + r * nq), ga = ld_stream4(g4 + r * nq);
+      const float4 xb = ld_stream4(x4 + (r + 1) * nq), gb = ld_stream4(g4 + (r + 1) * nq);
+      float4 o;
+      o.x = bwd1<ROUNDING>(xa.x, ga.x, p[0], lo_term[0], hi_term[0], a[0], rounding);
+      o.y = bwd1<ROUNDING>(xa.y, ga.y, p[1 % VEC], lo_term[1 % VEC], hi_term[1 % VEC], a[1 % VEC], rounding);
+      o.z = bwd1<ROUNDING>(xa.z, ga.z, p[2 % VEC], lo_term[2 % VEC], hi_term[2 % VEC], a[2 % VEC], rounding);
+      o.w = bwd1<ROUNDING>(xa.w, ga.w, p[3 % VEC], lo_term[3 % VEC], hi_term[3 % VEC], a[3 % VEC], rounding);
+      st_stream4(o4 + r * nq, o);
+      o.x = bwd1<ROUNDING>(xb.x, gb.x, p[0], lo_term[0], hi_term[0], a[0], rounding);
+      o.y = bwd1<ROUNDING>(xb.y, gb.y, p[1 % VEC], lo_term[1 % VEC], hi_term[1 % VEC], a[1 % VEC], rounding);
+      o.z = bwd1<ROUNDING>(xb.z, gb.z, p[2 % VEC], lo_term[2 % VEC], hi_term[2 % VEC], a[2 % VEC], rounding);
+      o.w = bwd1<ROUNDING>(xb.w, gb.w, p[3 % VEC], lo_term[3 % VEC], hi_term[3 % VEC], a[3 % VEC], rounding);
+      st_stream4(o4 + (r + 1) * nq, o);
+      if ((k += 2) >= 256) {  // bound the fp32 accumulation length
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { d0[j] += a[j].gs; d1[j] += a[j].gzp; a[j].gs = a[j].gzp = 0.f; }
+        k = 0;
+      }
+    }
+    for (; r < r1; ++r) {
+      const float4 xa = ld_stream4(x4 + r * nq), ga = ld_stream4(g4 + r * nq);
+      float4 o;
+      o.x = bwd1<ROUNDING>(xa.x, ga.x, p[0], lo_term[0], hi_term[0], a[0], rounding);
+      o.y = bwd1<ROUNDING>(xa.y, ga.y, p[1 % VEC], lo_term[1 % VEC], hi_term[1 % VEC], a[1 % VEC], rounding);
+      o.z = bwd1<ROUNDING>(xa.z, ga.z, p[2 % VEC], lo_term[2 % VEC], hi_term[2 % VEC], a[2 % VEC], rounding);
+      o.w = bwd1<ROUNDING>(xa.w, ga.w, p[3 % VEC], lo_term[3 % VEC], hi_term[3 % VEC], a[3 % VEC], rounding);
+      st_stream4(o4 + r * nq, o);
+    }
+  } else {
+    for (long long r = r0; r < r1; ++r) {
+      const long long e = r * channels + q;
+      gx[e] = bwd1<ROUNDING>(__ldcs(x + e), __ldcs(gy + e), p[0], lo_term[0], hi_term[0], a[0], rounding);
+      if (++k == 256) { d0[0] += a[0].gs; d1[0] += a[0].gzp; a[0].gs = a[0].gzp = 0.f; k = 0; }
     }
   }
-  d0 += a.gs;
-  d1 += a.gzp;
-  if (partial) partial[(long long)blockIdx.y * channels + c] = make_double2(d0, d1);
+  if (partial) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      partial[(long long)blockIdx.y * channels + q * VEC + j] = make_double2(d0[j] + a[j].gs, d1[j] + a[j].gzp);
+  }
 }
 
 __global__ void bwd_cols_finish_kernel(const double2* __restrict__ partial, int nblocks, int channels,
@@ -217,7 +282,7 @@ static inline int persistent_grid(long long tiles, int ctas_per_sm) {
 }
 
 static inline long long cols_row_blocks(long long outer, long long channels) {
-  const long long gx = (channels + 127) / 128;
+  const long long gx = (((channels % 4 == 0) ? channels / 4 : channels) + 127) / 128;
   long long want = ((long long)sm_count() * 8 + gx - 1) / gx;
   if (want > outer) want = outer;
   if (want > 65535) want = 65535;
@@ -251,11 +316,19 @@ static int bwd_dispatch(const float* x, const float* scale, const float* zp, con
   if (inner == 1 && channels > 1) {
     const long long nb = cols_row_blocks(outer, channels);
     const long long rpb = (outer + nb - 1) / nb;
-    const dim3 grid((unsigned)((channels + 127) / 128), (unsigned)nb);
-    if (rounding == 0)
-      bwd_cols_kernel<0><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, rounding, partial);
-    else
-      bwd_cols_kernel<-1><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, rounding, partial);
+    const bool vec = (channels % 4 == 0) && aligned16(x) && aligned16(gy) && aligned16(gx);
+    // cols_row_blocks sizes the grid for the vector layout when C % 4 == 0; the scalar fallback only
+    // gets more thread blocks along x, the partial layout [row block][C] is the same.
+    const long long nqv = vec ? channels / 4 : channels;
+    const dim3 grid((unsigned)((nqv + 127) / 128), (unsigned)nb);
+#define SB_GOC(V_, R_) \
+  bwd_cols_kernel<V_, R_><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, rounding, partial)
+    if (vec) {
+      if (rounding == 0) SB_GOC(4, 0); else SB_GOC(4, -1);
+    } else {
+      if (rounding == 0) SB_GOC(1, 0); else SB_GOC(1, -1);
+    }
+#undef SB_GOC
     SB_LAUNCHED();
     if (need_red) {
       bwd_cols_finish_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(partial, (int)nb, (int)channels, gs, gzp);
@@ -278,9 +351,7 @@ static int bwd_dispatch(const float* x, const float* scale, const float* zp, con
 #undef SB_GO
   SB_LAUNCHED();
   if (need_red) {
-    const long long warps = channels;
-    bwd_rows_finish_kernel<<<(unsigned)((warps * 32 + kThreads - 1) / kThreads), kThreads, 0, st>>>(
-        partial, outer, (int)channels, tpr, gs, gzp);
+    bwd_rows_finish_kernel<<<(unsigned)channels, kThreads, 0, st>>>(partial, outer, (int)channels, tpr, gs, gzp);
     SB_LAUNCHED();
   }
   return SB200_OK;

@@ -149,7 +149,9 @@ __device__ __forceinline__ float round_q(float v, int rounding) {
 //   0.5 - |q1 - t1| <= |q1| * 2^-22.  Those elements (a ~1e-4 fraction for 8-bit data), huge or
 //   non-finite quotients, and out-of-range scales take the exact fp64 route.
 // Verified against rintf(x / s) on 4e9 random + adversarial (k + 0.5) * s +- few-ulp inputs.
-template <int ROUNDING>
+// LAZY: p.rs is not populated (per-channel parameters come from a shared-memory table holding only
+// s, 1/s, zp); the rare exact fallback computes the fp64 reciprocal on the spot.
+template <int ROUNDING, bool LAZY = false>
 __device__ __forceinline__ float quant_round(float x, const QP& p, int rounding) {
   if (ROUNDING == 0 && p.fast) {
     const float q0 = __fmul_rn(x, p.r);
@@ -160,12 +162,13 @@ __device__ __forceinline__ float quant_round(float x, const QP& p, int rounding)
     const float c = __fmaf_rn(fabsf(q1), -0x1p-22f, __fsub_rn(0.5f, fabsf(d)));
     if (c > 0.f) return t1;
   }
+  if (LAZY) return round_q<ROUNDING>(__double2float_rn(__dmul_rn((double)x, __drcp_rn((double)p.s))), rounding);
   return round_q<ROUNDING>(div_exact(x, p), rounding);
 }
 
-template <int ROUNDING>
+template <int ROUNDING, bool LAZY = false>
 __device__ __forceinline__ float qdq1(float x, const QP& p, int rounding) {
-  float v = __fadd_rn(quant_round<ROUNDING>(x, p, rounding), p.zp);
+  float v = __fadd_rn(quant_round<ROUNDING, LAZY>(x, p, rounding), p.zp);
   v = fmax_nan(fmin_nan(v, p.qmax), p.qmin);
   return __fmul_rn(__fsub_rn(v, p.zp), p.s);
 }

@@ -14,6 +14,7 @@ size_t gptq4_tc_workspace(long long M, long long K, long long N, int group_size)
 int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
              long long K, long long N, long long KW, int group_size, void* workspace, size_t workspace_bytes,
              cudaStream_t st);
+void gptq4_tc_set_trace(long long* p);
 static int g_gptq_impl = 0;
 }  // namespace sb200
 
@@ -24,6 +25,11 @@ extern "C" {
 int sb200_gptq4_set_impl(int impl) {
   SB_REQUIRE(impl >= 0 && impl <= 2, "sb200_gptq4_set_impl: impl must be 0, 1 or 2 (got %d)", impl);
   g_gptq_impl = impl;
+  return SB200_OK;
+}
+
+int sb200_gptq4_set_trace(int64_t* device_buffer) {
+  gptq4_tc_set_trace(reinterpret_cast<long long*>(device_buffer));
   return SB200_OK;
 }
 

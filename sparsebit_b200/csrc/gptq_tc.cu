@@ -16,8 +16,9 @@
 // Pipeline (one CTA = one 128 x 128 output tile, 16 warps, 1 CTA / SM):
 //   warp 0      TMA producer: per 64-K stage one bulk-tensor load each for A_hi, A_lo (128x64 fp16,
 //               SWIZZLE_128B) and for the PACKED weight tile (8 x 128 int32 = 4 KB)
-//   warps 12-15 unpack: packed words (shared) -> fp16 B tile in the canonical K-major SWIZZLE_128B
-//               UMMA layout (one int32 = 8 nibbles = exactly one 16-byte swizzle chunk)
+//   warps 12-19 unpack (two sets of 4 warps alternating stages, so one set's proxy fence / load
+//               latency overlaps the other's ALU work): packed words (shared) -> fp16 B tile in the
+//               canonical K-major SWIZZLE_128B UMMA layout (one int32 = 8 nibbles = one 16-byte chunk)
 //   warp 1      MMA issuer: 4 x (hi, lo) tcgen05.mma.kind::f16 128x128x16 per stage, fp32 accumulators
 //               in TMEM, double buffered per K group; tcgen05.commit releases stages / publishes groups
 //   warps 4-11  epilogue: tcgen05.ld the group's 128x128 partial sums, fold in scale / zero / row sums
@@ -39,7 +40,7 @@ constexpr int kTileN = 128;
 constexpr int kBlockK = 64;   // fp16 elements per stage = one 128-byte swizzle atom
 constexpr int kStages = 4;
 constexpr int kGroupK = 128;  // epilogue granularity (= the reference's BLOCKLEN)
-constexpr int kTcThreads = 512;
+constexpr int kTcThreads = 640;  // 5 warpgroups: control | epilogue x2 | unpack x2
 constexpr uint32_t kTmemCols = 256;  // 2 accumulator buffers x 128 fp32 columns
 
 constexpr int kABytes = kTileM * kBlockK * 2;      // 16 KB  (hi or lo)
@@ -87,6 +88,19 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accum)
       : "memory");
 }
+// elect.sync: exactly one lane of a converged warp gets `true`.  Unlike `lane == 0` the compiler knows the
+// guarded code runs on a single lane of a uniform warp and keeps tcgen05 operands in uniform registers
+// (no per-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY lane loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -101,6 +115,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Register re-balancing between warpgroups (the kernel is launched with 65536 / 640 -> 96 registers per
+// thread; the epilogue needs ~130 for its 64 accumulators, the other roles far fewer).
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major) | [32,46) SBO >> 4 = 1024 B
@@ -119,7 +140,8 @@ constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint
 // row over K group g, rowscale[m] = 2^e.
 __global__ void __launch_bounds__(256) gptq_split_kernel(const float* __restrict__ x, __half* __restrict__ a_hi,
                                                          __half* __restrict__ a_lo, float* __restrict__ xsum,
-                                                         float* __restrict__ rowscale, int K, int G) {
+                                                         float* __restrict__ rowscale, int* __restrict__ need_lo,
+                                                         int K, int G) {
   __shared__ float red[8];
   const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float* xr = x + (size_t)m * K;
@@ -141,6 +163,7 @@ __global__ void __launch_bounds__(256) gptq_split_kernel(const float* __restrict
   const float down = ldexpf(1.f, -e);
   if (tid == 0) rowscale[m] = ldexpf(1.f, e);
   const int nchunk = K >> 3;
+  bool any_lo = false;
   for (int c0 = 0; c0 < nchunk; c0 += 256) {
     const int c = c0 + tid;
     float s = 0.f;
@@ -153,6 +176,7 @@ __global__ void __launch_bounds__(256) gptq_split_kernel(const float* __restrict
       for (int j = 0; j < 8; ++j) {
         hi[j] = __float2half_rn(v[j]);
         lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+        any_lo |= (__half_as_ushort(lo[j]) & 0x7FFFu) != 0;
         s += v[j];
       }
       *reinterpret_cast<uint4*>(a_hi + (size_t)m * K + c * 8) = *reinterpret_cast<const uint4*>(hi);
@@ -163,6 +187,27 @@ __global__ void __launch_bounds__(256) gptq_split_kernel(const float* __restrict
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((lane & 15) == 0 && (c >> 4) < G) xsum[(size_t)m * G + (c >> 4)] = s;
   }
+  // activations that are exactly fp16-representable after the row scaling (the reference's model path
+  // feeds fp16 activations cast to fp32, utils/quant.py:262-277) leave lo == 0 everywhere: the GEMM then
+  // skips the second MMA pass and its TMA traffic, with bit-identical results.
+  if (__any_sync(0xffffffffu, any_lo) && lane == 0) atomicOr(need_lo, 1);
+}
+
+// ---------------------------------------------------------------------------------- zero-point probe
+// GPTQ checkpoints store zeros = zero * scale with an INTEGER zero (utils/quant.py:188, find_params
+// :83-89).  When that holds for every (n, g), (q - zero) is an exact fp16 integer that can go into the
+// MMA directly and the epilogue needs a single FMA per element.  The probe recovers zero = rint(z/s),
+// verifies |z - zero*s| <= 2^-20 |z| (fp32 rounding of the product is 2^-24) and |zero| <= 1024, and
+// clears *flag otherwise -- then the kernel uses the general (scale, zeros) epilogue.
+__global__ void gptq_zero_probe_kernel(const float* __restrict__ scales, const float* __restrict__ zeros, long long n,
+                                       __half* __restrict__ zint, int* __restrict__ flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = scales[i], z = zeros[i];
+  const float zi = rintf(z / s);
+  const bool ok = (fabsf(zi) <= 1024.f) && (fabsf(fmaf(-zi, s, z)) <= fabsf(z) * 0x1p-20f + 1e-30f);
+  zint[i] = __float2half_rn(ok ? zi : 0.f);
+  if (!ok) atomicAnd(flag, 0);
 }
 
 // ---------------------------------------------------------------------------------- main kernel
@@ -170,7 +215,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                 const __grid_constant__ CUtensorMap map_q, float* __restrict__ out, const float* __restrict__ scales,
                 const float* __restrict__ zeros, const float* __restrict__ xsum, const float* __restrict__ rowscale,
-                int M, int K, int N, int Gq, int G128, int group_size) {
+                const __half* __restrict__ zint, const int* __restrict__ int_zero_flag, int M, int K, int N, int Gq,
+                int G128, int group_size, long long* __restrict__ trace) {
   extern __shared__ unsigned char smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), bookkeeping after them
   unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -179,6 +225,11 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * kTileN;
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   const int num_g = (num_kb + 1) / 2;  // 128-K groups
+  const bool int_zero = int_zero_flag[0] != 0;  // uniform: every zeros[n,g] is an integer multiple of scales[n,g]
+  const bool need_lo = int_zero_flag[1] != 0;   // uniform: some activation has a non-zero fp16 low part
+  // optional pipeline trace (sb200_gptq4_set_trace): CTA (0,0) stamps clock64() at each handoff, [event][stage]
+  long long* tr = (trace && blockIdx.x == 0 && blockIdx.y == 0) ? trace : nullptr;
+#define SB_TRACE(ev, idx) do { if (tr && (idx) < 256) tr[(ev) * 256 + (idx)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
@@ -188,7 +239,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->bready[s], 4);  // one arrive per unpack warp
+      mbar_init(&sm->bready[s], 4);  // one arrive per warp of the unpack set that owns the stage
       mbar_init(&sm->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -208,6 +259,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
 
+  if (warp < 4) reg_dec<56>();
   if (warp == 0) {
     // ================================================================== TMA producer
     if (lane == 0) {
@@ -215,70 +267,121 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         const int s = kb % kStages;
         const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
         mbar_wait(&sm->empty[s], ph ^ 1u);
+        SB_TRACE(0, kb);
         unsigned char* st = stage_base + (size_t)s * kStageBytes;
-        mbar_expect_tx(&sm->full[s], kTxBytes);
+        mbar_expect_tx(&sm->full[s], need_lo ? kTxBytes : kTxBytes - kABytes);
         tma_load_2d(st, &map_hi, kb * kBlockK, m0, &sm->full[s]);
-        tma_load_2d(st + kABytes, &map_lo, kb * kBlockK, m0, &sm->full[s]);
+        if (need_lo) tma_load_2d(st + kABytes, &map_lo, kb * kBlockK, m0, &sm->full[s]);
         tma_load_2d(st + 2 * kABytes + kBBytes, &map_q, n0, kb * (kBlockK / 8), &sm->full[s]);
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-      const int g = kb >> 1, b = g & 1;
-      if ((kb & 1) == 0) {  // first stage of a K group: the accumulator buffer must have been drained
-        mbar_wait(&sm->tmem_empty[b], (((uint32_t)(g >> 1)) & 1u) ^ 1u);
-      }
-      mbar_wait(&sm->full[s], ph);
-      mbar_wait(&sm->bready[s], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_hi = smem_u32(stage_base + (size_t)s * kStageBytes);
-        const uint32_t a_lo = a_hi + kABytes;
-        const uint32_t b_sm = a_hi + 2 * kABytes;
-        const uint32_t d = tmem_base + (uint32_t)(b * kTileN);
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t bd = umma_desc_sw128(b_sm + k * 32);
-          tc_mma_f16(d, umma_desc_sw128(a_hi + k * 32), bd, kIdesc, !((kb & 1) == 0 && k == 0));
-          tc_mma_f16(d, umma_desc_sw128(a_lo + k * 32), bd, kIdesc, true);
+    // (Measured with the clock64 trace: a `lane == 0` issue region cost 550-750 cycles of issue overhead
+    // per stage against 256-512 cycles of tensor-core work.)
+    // The whole warp runs the (uniform) control flow and descriptor arithmetic; one elected lane issues.
+    // bready[s] is only completed by warps that already observed full[s], so it implies the TMA data landed.
+    {
+      const uint32_t stage0 = smem_u32(stage_base);
+      const uint64_t dconst = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        const int g = kb >> 1, b = g & 1;
+        if ((kb & 1) == 0) {  // first stage of a K group: the accumulator buffer must have been drained
+          mbar_wait(&sm->tmem_empty[b], (((uint32_t)(g >> 1)) & 1u) ^ 1u);
         }
-        tc_commit(&sm->empty[s]);                                        // stage reusable when these MMAs finish
-        if ((kb & 1) == 1 || kb == num_kb - 1) tc_commit(&sm->tmem_full[b]);  // group complete
+        mbar_wait(&sm->bready[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = stage0 + (uint32_t)s * kStageBytes;
+        const uint64_t da = dconst | (uint64_t)((a_hi >> 4) & 0x3FFFu);
+        const uint64_t dl = dconst | (uint64_t)(((a_hi + kABytes) >> 4) & 0x3FFFu);
+        const uint64_t db = dconst | (uint64_t)(((a_hi + 2 * kABytes) >> 4) & 0x3FFFu);
+        const uint32_t d = tmem_base + (uint32_t)(b * kTileN);
+        if (elect_one()) {
+          SB_TRACE(3, kb);
+          if (need_lo) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {  // +2 in the address field = 32 bytes = 16 fp16 along K
+              tc_mma_f16(d, da + 2 * k, db + 2 * k, kIdesc, !((kb & 1) == 0 && k == 0));
+              tc_mma_f16(d, dl + 2 * k, db + 2 * k, kIdesc, true);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              tc_mma_f16(d, da + 2 * k, db + 2 * k, kIdesc, !((kb & 1) == 0 && k == 0));
+          }
+          SB_TRACE(4, kb);
+          tc_commit(&sm->empty[s]);                                            // stage reusable when these MMAs finish
+          if ((kb & 1) == 1 || kb == num_kb - 1) tc_commit(&sm->tmem_full[b]);  // group complete
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp >= 12) {
     // ================================================================== unpack: packed int4 -> fp16 UMMA tile
-    const int t = threadIdx.x - 12 * 32;  // 0..127 = column of the tile
-    for (int kb = 0; kb < num_kb; ++kb) {
+    reg_dec<56>();
+    const int t = (threadIdx.x - 12 * 32) & 127;  // column of the tile
+    const int uset = (warp - 12) >> 2;             // this set handles stages kb with (kb & 1) == uset
+    // integer zero point of this column per K stage, fetched one iteration (two stages) ahead of its use;
+    // the group index is advanced incrementally (no division in the loop)
+    int gq_next = (uset * kBlockK) / group_size;
+    int koff_next = uset * kBlockK;
+    auto zint_fetch = [&](int kb) -> float {
+      if (!int_zero || n0 + t >= N || kb >= num_kb) return 0.f;
+      return __half2float(__ldg(zint + (size_t)(n0 + t) * Gq + gq_next));
+    };
+    float z_cur = zint_fetch(uset);
+    for (int kb = uset; kb < num_kb; kb += 2) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+      koff_next += 2 * kBlockK;
+      while (koff_next >= (gq_next + 1) * group_size) ++gq_next;
+      const float z_next = zint_fetch(kb + 2);
       mbar_wait(&sm->full[s], ph);
+      if (t == 0 && (warp & 3) == 0) SB_TRACE(1, kb);
       unsigned char* st = stage_base + (size_t)s * kStageBytes;
       const uint32_t* bq = reinterpret_cast<const uint32_t*>(st + 2 * kABytes + kBBytes);
       unsigned char* brow = st + 2 * kABytes + (size_t)t * 128;  // row t of the B tile (64 fp16 = 128 B)
+      // all 8 packed words first: the loads must not be interleaved with the stores below (both are
+      // shared-memory accesses the compiler cannot disambiguate, which serialised 8 LDS->ALU->STS chains)
+      uint32_t w[kBlockK / 8];
+#pragma unroll
+      for (int r = 0; r < kBlockK / 8; ++r) w[r] = bq[r * kTileN + t];
+      // subtrahend: 1024 (the 0x6400 bias) plus, in integer-zero mode, the group's zero point
+      const float zsub = 1024.f + z_cur;
+      z_cur = z_next;
+      const __half2 sub = __float2half2_rn(zsub);
+      const __half2 sub16 = __float2half2_rn(zsub);  // same value; the x16 lanes are rescaled by an exact FMA
+      const __half2 k16 = __float2half2_rn(0.0625f);
 #pragma unroll
       for (int r = 0; r < kBlockK / 8; ++r) {
-        const uint32_t w = bq[r * kTileN + t];
-        // halves (n0,n4) (n1,n5) (n2,n6) (n3,n7): 0x6400 | q is the fp16 number 1024 + q
-        uint32_t h[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t v = ((w >> (4 * j)) & 0x000F000Fu) | 0x64006400u;
-          const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x6400)));
-          h[j] = *reinterpret_cast<const uint32_t*>(&hv);
-        }
-        *reinterpret_cast<uint4*>(brow + ((r ^ (t & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+        // halves (n0,n4) (n1,n5) (n2,n6) (n3,n7).  0x6400 | q is the fp16 number 1024 + q; for the odd
+        // nibbles the mask is applied in place (bits 4..7): 0x6400 | (q << 4) = 1024 + 16 q, brought back by
+        // one exact HFMA2: (1024 + 16 q) / 16 - (64 + zero) ... folded as v * 1/16 + (64 - zsub) - 64 below.
+        const uint32_t lo = w[r], hi = w[r] >> 8;
+        const uint32_t v0 = (lo & 0x000F000Fu) | 0x64006400u;  // (n0, n4)
+        const uint32_t v1 = (lo & 0x00F000F0u) | 0x64006400u;  // 1024 + 16 * (n1, n5)
+        const uint32_t v2 = (hi & 0x000F000Fu) | 0x64006400u;  // (n2, n6)
+        const uint32_t v3 = (hi & 0x00F000F0u) | 0x64006400u;  // 1024 + 16 * (n3, n7)
+        // (1024 + 16 q) * 1/16 = 64 + q exactly;  64 + q - (zsub - 960) = q - (zsub - 1024)
+        const __half2 off = __hsub2(sub16, __float2half2_rn(960.f));
+        const __half2 h0 = __hsub2(*reinterpret_cast<const __half2*>(&v0), sub);
+        const __half2 h1 = __hfma2(*reinterpret_cast<const __half2*>(&v1), k16, __hneg2(off));
+        const __half2 h2 = __hsub2(*reinterpret_cast<const __half2*>(&v2), sub);
+        const __half2 h3 = __hfma2(*reinterpret_cast<const __half2*>(&v3), k16, __hneg2(off));
+        *reinterpret_cast<uint4*>(brow + ((r ^ (t & 7)) << 4)) =
+            make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->bready[s]);
+      if (t == 0 && (warp & 3) == 0) SB_TRACE(2, kb);
     }
   } else if (warp >= 4) {
     // ================================================================== epilogue (8 warps)
+    reg_inc<152>();  // (152-96)*256 <= (96-56)*384: must fit what the other warpgroups released
     const int e = threadIdx.x - 4 * 32;           // 0..255
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;              // which 64 columns
@@ -309,13 +412,16 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const int b = g & 1;
       if (g + 1 < num_g) fetch(g + 1, v_next, xs_next);
       mbar_wait(&sm->tmem_full[b], ((uint32_t)(g >> 1)) & 1u);
+      if (e == 0) SB_TRACE(5, g);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kTileN + col0);
       const float4* sc4 = reinterpret_cast<const float4*>(&sm->sc[b][col0]);
       const float4* zr4 = reinterpret_cast<const float4*>(&sm->zr[b][col0]);
-      const float nxs = -xs;
+      const float nxs = int_zero ? 0.f : -xs;  // integer-zero mode: the zero point is already inside the MMA
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        // 32 columns at a time (requesting both halves up front was measured slower: 100 ms vs 78 ms per
+        // LLaMA-7B prefill, the extra 32 live registers cost more than the second TMEM round trip)
         uint32_t p[32];
         tc_ld32(taddr + 32 * hh, p);
         tc_wait_ld();
@@ -324,14 +430,26 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm->tmem_empty[b]);
         }
+        if (int_zero) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 s4 = sc4[8 * hh + j4], z4 = zr4[8 * hh + j4];
-          const int o = 32 * hh + 4 * j4;
-          acc[o + 0] = fmaf(s4.x, __uint_as_float(p[4 * j4 + 0]), fmaf(z4.x, nxs, acc[o + 0]));
-          acc[o + 1] = fmaf(s4.y, __uint_as_float(p[4 * j4 + 1]), fmaf(z4.y, nxs, acc[o + 1]));
-          acc[o + 2] = fmaf(s4.z, __uint_as_float(p[4 * j4 + 2]), fmaf(z4.z, nxs, acc[o + 2]));
-          acc[o + 3] = fmaf(s4.w, __uint_as_float(p[4 * j4 + 3]), fmaf(z4.w, nxs, acc[o + 3]));
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s4 = sc4[8 * hh + j4];
+            const int o = 32 * hh + 4 * j4;
+            acc[o + 0] = fmaf(s4.x, __uint_as_float(p[4 * j4 + 0]), acc[o + 0]);
+            acc[o + 1] = fmaf(s4.y, __uint_as_float(p[4 * j4 + 1]), acc[o + 1]);
+            acc[o + 2] = fmaf(s4.z, __uint_as_float(p[4 * j4 + 2]), acc[o + 2]);
+            acc[o + 3] = fmaf(s4.w, __uint_as_float(p[4 * j4 + 3]), acc[o + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s4 = sc4[8 * hh + j4], z4 = zr4[8 * hh + j4];
+            const int o = 32 * hh + 4 * j4;
+            acc[o + 0] = fmaf(s4.x, __uint_as_float(p[4 * j4 + 0]), fmaf(z4.x, nxs, acc[o + 0]));
+            acc[o + 1] = fmaf(s4.y, __uint_as_float(p[4 * j4 + 1]), fmaf(z4.y, nxs, acc[o + 1]));
+            acc[o + 2] = fmaf(s4.z, __uint_as_float(p[4 * j4 + 2]), fmaf(z4.z, nxs, acc[o + 2]));
+            acc[o + 3] = fmaf(s4.w, __uint_as_float(p[4 * j4 + 3]), fmaf(z4.w, nxs, acc[o + 3]));
+          }
         }
       }
       if (g + 1 < num_g) {
@@ -340,6 +458,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         xs = xs_next;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (e == 0) SB_TRACE(6, g);
     }
     // out[m, n] += rowscale[m] * acc   (out is pre-initialised with the bias by the caller)
     if (m < M) {
@@ -405,18 +524,23 @@ static bool make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* ba
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct TcWorkspace {
-  size_t off_hi, off_lo, off_xsum, off_rs, total;
+  size_t off_hi, off_lo, off_xsum, off_rs, off_zint, off_flag, total;
 };
-static TcWorkspace tc_layout(long long M, long long K) {
+static TcWorkspace tc_layout(long long M, long long K, long long N = 0, long long Gq = 0) {
   TcWorkspace w;
   const long long G128 = (K + kGroupK - 1) / kGroupK;
   w.off_hi = 0;
   w.off_lo = align_up((size_t)M * K * 2, 1024);
   w.off_xsum = w.off_lo + align_up((size_t)M * K * 2, 1024);
   w.off_rs = w.off_xsum + align_up((size_t)M * G128 * 4, 1024);
-  w.total = w.off_rs + align_up((size_t)M * 4, 1024);
+  w.off_zint = w.off_rs + align_up((size_t)M * 4, 1024);
+  w.off_flag = w.off_zint + align_up((size_t)N * Gq * 2, 1024);
+  w.total = w.off_flag + 1024;
   return w;
 }
+
+static long long* g_tc_trace = nullptr;
+void gptq4_tc_set_trace(long long* p) { g_tc_trace = p; }
 
 bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
                         long long KW, int group_size) {
@@ -432,13 +556,14 @@ bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out
 
 size_t gptq4_tc_workspace(long long M, long long K, long long N, int group_size) {
   if (K % 8 != 0 || N % 4 != 0 || group_size % kGroupK != 0) return 0;
-  return tc_layout(M, K).total + 1024;
+  return tc_layout(M, K, N, (K + group_size - 1) / group_size).total + 1024;
 }
 
 int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
              long long K, long long N, long long KW, int group_size, void* workspace, size_t workspace_bytes,
              cudaStream_t st) {
-  const TcWorkspace w = tc_layout(M, K);
+  const int Gq = (int)((K + group_size - 1) / group_size);
+  const TcWorkspace w = tc_layout(M, K, N, Gq);
   unsigned char* ws = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   if (!workspace || (size_t)(ws - reinterpret_cast<unsigned char*>(workspace)) + w.total > workspace_bytes) {
     set_error("gptq4_tc: workspace too small");
@@ -448,10 +573,15 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
   __half* a_lo = reinterpret_cast<__half*>(ws + w.off_lo);
   float* xsum = reinterpret_cast<float*>(ws + w.off_xsum);
   float* rowscale = reinterpret_cast<float*>(ws + w.off_rs);
+  __half* zint = reinterpret_cast<__half*>(ws + w.off_zint);
+  int* flag = reinterpret_cast<int*>(ws + w.off_flag);
   const int G128 = (int)((K + kGroupK - 1) / kGroupK);
-  const int Gq = (int)((K + group_size - 1) / group_size);
 
-  gptq_split_kernel<<<(unsigned)M, 256, 0, st>>>(x, a_hi, a_lo, xsum, rowscale, (int)K, G128);
+  SB_CUDA(cudaMemsetAsync(flag, 0xFF, sizeof(int), st));      // [0] assume integer zero points until disproved
+  SB_CUDA(cudaMemsetAsync(flag + 1, 0, sizeof(int), st));     // [1] need_lo: set by the split kernel
+  gptq_zero_probe_kernel<<<(unsigned)(((long long)N * Gq + 255) / 256), 256, 0, st>>>(scales, zeros, (long long)N * Gq, zint, flag);
+  SB_LAUNCHED();
+  gptq_split_kernel<<<(unsigned)M, 256, 0, st>>>(x, a_hi, a_lo, xsum, rowscale, flag + 1, (int)K, G128);
   SB_LAUNCHED();
 
   CUtensorMap map_hi, map_lo, map_q;
@@ -472,8 +602,8 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
     attr_done = true;
   }
   const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)((N + kTileN - 1) / kTileN));
-  gptq4_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_hi, map_lo, map_q, out, scales, zeros, xsum, rowscale, (int)M,
-                                                  (int)K, (int)N, Gq, G128, group_size);
+  gptq4_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_hi, map_lo, map_q, out, scales, zeros, xsum, rowscale, zint, flag,
+                                                  (int)M, (int)K, (int)N, Gq, G128, group_size, g_tc_trace);
   SB_LAUNCHED();
   return SB200_OK;
 }

@@ -60,18 +60,74 @@ __global__ void __launch_bounds__(kThreads) minmax_rows_cta_kernel(const float* 
   }
 }
 
-// Regime B: short rows -- one warp per row.
+// Regime B: mid-length rows (64 < inner < 4096) -- a warp takes 4 consecutive rows per iteration and
+// keeps one 128-bit load per row in flight per lane (one row alone is only a few hundred bytes).
 __global__ void __launch_bounds__(kThreads) minmax_rows_warp_kernel(const float* __restrict__ x, long long rows,
                                                                     long long inner, int channels,
                                                                     uint32_t* __restrict__ state) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
-    MinMaxAcc acc;
-    acc.init();
-    span_minmax(x + row * inner, inner, lane, 32, acc);
-    acc.warp_reduce();
-    if (lane == 0) acc.publish(state + 2 * (row % channels));
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const bool vec = ((inner & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+  for (long long row0 = gw * 4; row0 < rows; row0 += warps * 4) {
+    MinMaxAcc acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j].init();
+    if (vec && row0 + 3 < rows) {
+      const long long nv = inner >> 2;
+      const float4* base = reinterpret_cast<const float4*>(x + row0 * inner);
+      for (long long i = lane; i < nv; i += 32) {
+        const float4 v0 = ld_stream4(base + i), v1 = ld_stream4(base + nv + i), v2 = ld_stream4(base + 2 * nv + i),
+                     v3 = ld_stream4(base + 3 * nv + i);
+        acc[0].add4(v0); acc[1].add4(v1); acc[2].add4(v2); acc[3].add4(v3);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (row0 + j < rows) span_minmax(x + (row0 + j) * inner, inner, lane, 32, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j].warp_reduce();
+      if (lane == 0 && row0 + j < rows) acc[j].publish(state + 2 * ((row0 + j) % channels));
+    }
+  }
+}
+
+// Regime B': tiny rows (inner <= 64, e.g. 7x7 feature maps) -- a warp stages 32 consecutive rows
+// (one contiguous chunk, read with full coalescing) in shared memory, then lane l reduces row l.
+__global__ void __launch_bounds__(kThreads) minmax_rows_tiny_kernel(const float* __restrict__ x, long long rows,
+                                                                    int inner, int channels,
+                                                                    uint32_t* __restrict__ state) {
+  extern __shared__ __align__(16) float s_rows[];  // [warps per CTA][32 * inner]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* mine = s_rows + (size_t)wid * 32 * inner;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool base_ok = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+  for (long long row0 = ((((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * 32; row0 < rows; row0 += warps * 32) {
+    const int nrows = (int)((rows - row0) < 32 ? (rows - row0) : 32);
+    const int cnt = nrows * inner;
+    const float* src = x + row0 * inner;
+    if (base_ok && ((cnt & 3) == 0) && (((row0 * inner) & 3) == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(mine);
+      for (int i = lane; i < (cnt >> 2); i += 32) d4[i] = ld_stream4(s4 + i);
+    } else {
+      for (int i = lane; i < cnt; i += 32) mine[i] = __ldcs(src + i);
+    }
+    __syncwarp();
+    if (lane < nrows) {
+      MinMaxAcc acc;
+      acc.init();
+      const float* r = mine + lane * inner;
+      const bool rot = (inner & 1) == 0;  // even row pitch: rotate the start column to spread banks
+      for (int i = 0; i < inner; ++i) {
+        const int col = rot ? (i + lane) % inner : i;
+        acc.add(r[col]);
+      }
+      acc.publish(state + 2 * ((row0 + lane) % channels));
+    }
+    __syncwarp();
   }
 }
 
@@ -536,8 +592,17 @@ int sb200_observe_minmax_perchannel(const float* x, int64_t outer, int64_t chann
   } else if (inner >= 4096) {
     const long long tiles = rows * ((inner + kRowTile - 1) / kRowTile);
     minmax_rows_cta_kernel<<<persistent_grid(tiles, 8), kThreads, 0, st>>>(x, rows, inner, (int)channels, state);
+  } else if (inner <= 64) {
+    const long long ctas = (rows + 32 * (kThreads / 32) - 1) / (32 * (kThreads / 32));
+    const size_t smem = (size_t)(kThreads / 32) * 32 * inner * sizeof(float);  // <= 64 KB
+    static bool attr_done = false;
+    if (!attr_done) {
+      SB_CUDA(cudaFuncSetAttribute(minmax_rows_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_done = true;
+    }
+    minmax_rows_tiny_kernel<<<persistent_grid(ctas, 3), kThreads, smem, st>>>(x, rows, (int)inner, (int)channels, state);
   } else {
-    const long long ctas = (rows + (kThreads / 32) - 1) / (kThreads / 32);
+    const long long ctas = (rows + 4 * (kThreads / 32) - 1) / (4 * (kThreads / 32));
     minmax_rows_warp_kernel<<<persistent_grid(ctas, 8), kThreads, 0, st>>>(x, rows, inner, (int)channels, state);
   }
   SB_LAUNCHED();

@@ -69,7 +69,18 @@ template <int MODE, int VEC, bool DOQ, bool STORE, bool STATS, bool MASK, int RO
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 stream_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, float* __restrict__ out,
               const float* __restrict__ scale, const float* __restrict__ zero_point, long long n,
-              float qmin, float qmax, int rounding, ChanGeom g, uint32_t* __restrict__ mm) {
+              float qmin, float qmax, int rounding, ChanGeom g, uint32_t* __restrict__ mm, int use_tab) {
+  // MODE_CHANNEL with use_tab: per-channel {scale, RN32(1/scale), rint(zp), in-range flag} staged once per
+  // CTA in shared memory (one LDS.128 per vector instead of two global loads + an fp64 reciprocal).
+  extern __shared__ __align__(16) float4 s_tab[];
+  if (DOQ && MODE == MODE_CHANNEL && use_tab) {
+    for (int ci = threadIdx.x; ci < g.channels; ci += blockDim.x) {
+      QP t;
+      t.set(__ldg(scale + ci), __ldg(zero_point + ci));
+      s_tab[ci] = make_float4(t.s, t.r, t.zp, t.fast ? 1.f : 0.f);
+    }
+    __syncthreads();
+  }
   const long long nvec = (VEC == 4) ? (n >> 2) : n;
   const long long T = (long long)gridDim.x * blockDim.x;
   long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,7 +133,27 @@ stream_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, flo
 #pragma unroll
             for (int j = 0; j < VEC; ++j) a[u][j] = qdq1<ROUNDING>(a[u][j], p, rounding);
           } else {  // MODE_CHANNEL
-            if (pos + (VEC - 1) < g.inner) {  // whole vector inside one channel row (fast path)
+            if (use_tab) {
+              if (pos + (VEC - 1) < g.inner) {  // whole vector inside one channel row
+                const float4 t = s_tab[c];
+                p.s = t.x; p.r = t.y; p.zp = t.z; p.fast = t.w != 0.f;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) a[u][j] = qdq1<ROUNDING, true>(a[u][j], p, rounding);
+              } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                  long long pj = pos + j;
+                  int cj = c;
+                  while (pj >= g.inner) {
+                    pj -= g.inner;
+                    cj = (cj + 1 == g.channels) ? 0 : cj + 1;
+                  }
+                  const float4 t = s_tab[cj];
+                  p.s = t.x; p.r = t.y; p.zp = t.z; p.fast = t.w != 0.f;
+                  a[u][j] = qdq1<ROUNDING, true>(a[u][j], p, rounding);
+                }
+              }
+            } else if (pos + (VEC - 1) < g.inner) {  // whole vector inside one channel row (fast path)
               if (c != c_loaded) {
                 p.set(__ldg(scale + c), __ldg(zero_point + c));
                 c_loaded = c;
@@ -399,9 +430,11 @@ static int launch_stream(const float* x, const uint8_t* mask, float* out, const 
   g.channels = (int)(channels > 0 ? channels : 1);
   g.dpos = step % g.inner;
   g.dc = (int)((step / g.inner) % g.channels);
+  const int use_tab = (MODE == MODE_CHANNEL && DOQ && channels <= 2048) ? 1 : 0;
+  const size_t tab_bytes = use_tab ? (size_t)channels * sizeof(float4) : 0;  // <= 32 KB
 #define SB_GO(VEC_, R_)                                                                         \
-  stream_kernel<MODE, VEC_, DOQ, STORE, STATS, MASK, R_><<<grid, kThreads, 0, st>>>(            \
-      x, mask, out, scale, zp, n, (float)qmin, (float)qmax, rounding, g, mm)
+  stream_kernel<MODE, VEC_, DOQ, STORE, STATS, MASK, R_><<<grid, kThreads, tab_bytes, st>>>(    \
+      x, mask, out, scale, zp, n, (float)qmin, (float)qmax, rounding, g, mm, use_tab)
   if (vec) {
     if (rounding == 0) SB_GO(4, 0); else SB_GO(4, -1);
   } else {

@@ -94,6 +94,44 @@ def test_tcgen05_path_vs_fp64_oracle(bshape, k, n, gs):
     np.testing.assert_array_less(np.abs(y - exp), 1e-5 + 1e-5 * rowmag * np.ones_like(exp))
 
 
+@pytest.mark.parametrize("m,k,n", [(256, 1024, 512), (77, 512, 132)])
+def test_tcgen05_fp16_representable_activations_single_pass(m, k, n):
+    """fp16 activations cast to fp32 (the reference's model path): lo == 0 everywhere, the kernel skips the
+    second MMA pass -- result must still match the oracle, and equal the 2-pass result on the same data."""
+    rng = np.random.default_rng(m + k)
+    x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, 128)
+    x = x.astype(np.float16).astype(np.float32)
+    lib = _lib.load()
+    lib.sb200_gptq4_set_impl(2)
+    try:
+        y = _run(x, qw, bias, scales, zeros, 128)
+        x2 = x.copy()
+        x2[0, 0] += 1e-5  # one element with a non-zero low part forces the 2-pass path
+        y2 = _run(x2, qw, bias, scales, zeros, 128)
+    finally:
+        lib.sb200_gptq4_set_impl(0)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (m, n)), scales, zeros, 128)
+    np.testing.assert_allclose(y, exp, **TOL)
+    np.testing.assert_allclose(y2[1:], y[1:], rtol=0, atol=0)  # rows without the perturbation: bit-identical
+
+
+def test_tcgen05_general_zero_points_fall_back_to_affine_epilogue():
+    """zeros that are NOT an integer multiple of scales (the contract allows any fp32 value): the
+    device-side probe must clear the integer-zero flag and the (scale, zeros) epilogue must be used."""
+    rng = np.random.default_rng(5)
+    x, qw, bias, scales, zeros = _make_case(rng, (200,), 1024, 384, 128)
+    zeros = (zeros + 0.37 * scales * rng.uniform(0.5, 1.5, zeros.shape)).astype(np.float32)
+    zeros[3, 2] = 0.0
+    lib = _lib.load()
+    lib.sb200_gptq4_set_impl(2)
+    try:
+        y = _run(x, qw, bias, scales, zeros, 128)
+    finally:
+        lib.sb200_gptq4_set_impl(0)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (200, 384)), scales, zeros, 128)
+    np.testing.assert_allclose(y, exp, **TOL)
+
+
 def test_tcgen05_forced_on_unsupported_shape_is_an_error():
     lib = _lib.load()
     rng = np.random.default_rng(1)
