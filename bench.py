@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gptq", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="enqueue the 109 launches eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -465,6 +466,26 @@ def main():
                "sample": f"all 109 sites at batch {sample_bs} instead of 256 ({elems} elems per pass, {len(times)} passes), torch CPU "
                          "op chain of quant_tensor.py:181-184 + min/max (oracle/torch_port.py)"}
 
+    # ---- secondary metric of BASELINE.json: GPTQ int4 g128 tok/s on the LLaMA-7B linear shapes ----------
+    gptq = None
+    if rank == 0 and world == 1 and not args.no_gptq:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_gptq
+
+            totals = bench_gptq.run([1, 2048], with_reference=True, quiet=True)
+            gptq = {"config": "LLaMA-7B, all 32 x 7 linears, int4 g128, fp16->fp32 activations, CUDA-graph timed, synthetic packed weights",
+                    "decode_tok_s": 1.0 / totals[(1, "ours_auto")], "prefill_2048_tok_s": 2048.0 / totals[(2048, "ours_auto")],
+                    "prefill_2048_useful_TFLOPs": 2 * 6_476_005_376 * 2048 / totals[(2048, "ours_auto")] / 1e12}
+            if (1, "reference_cuda") in totals:
+                gptq["reference_cuda_kernel"] = {"decode_tok_s": 1.0 / totals[(1, "reference_cuda")],
+                                                 "prefill_2048_tok_s": 2048.0 / totals[(2048, "reference_cuda")],
+                                                 "source": "oracle/_ref/gptq_ref.so built from /root/reference by oracle/build_ref.py"}
+                gptq["speedup_vs_reference_kernel"] = {"decode": totals[(1, "reference_cuda")] / totals[(1, "ours_auto")],
+                                                       "prefill_2048": totals[(2048, "reference_cuda")] / totals[(2048, "ours_auto")]}
+        except Exception as e:  # the headline line must still be printed
+            gptq = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -474,7 +495,7 @@ def main():
                        "parallelism": f"replicas x{world} (path has no exchange step; no data-path collective)",
                        "l2": "inputs larger than L2: 22 GB working set per step, every site owns its in/out buffers",
                        "launch": "2 CUDA graphs (55 activation sites + 1 init; 54 weight sites) replayed per step" if use_graphs else "eager launches"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "gptq": gptq,
         }
         print(json.dumps(line))
     if world > 1:

@@ -67,18 +67,25 @@ def timeit(fn, reps, copies=1):
     return e0.elapsed_time(e1) * 1e-3 / (nrep * copies)
 
 
-def main():
-    ref = load_ref()
+def run(ms, with_reference=True, quiet=False):
+    """Time all LLaMA-7B linear shapes at every M in `ms`; returns {(M, impl): seconds per forward over all
+    32 x 7 linears} and prints one JSON line per measurement unless quiet."""
+    ref = load_ref() if with_reference else None
     lib = _lib.load()
-    ms = [int(a) for a in sys.argv[1:]] or [1, 16, 2048]
     totals = {}
+
+    def emit(rec):
+        if not quiet:
+            print(json.dumps(rec))
+
+    fp16_acts = os.environ.get("SB200_FP16_ACTS", "1") == "1"
     for m in ms:
         for name, k, n, cnt in SHAPES:
             wbytes = k * n // 2
             copies = max(2, min(24, (256 << 20) // wbytes + 1)) if m <= 64 else 2
             ws = make(k, n, copies)
             x = torch.randn(m, k, device=dev)
-            if os.environ.get("SB200_FP16_ACTS", "1") == "1":
+            if fp16_acts:
                 # the reference's model path: fp16 activations cast to fp32 (utils/quant.py:262-277, SURVEY 8d)
                 x = x.half().float()
             y = torch.zeros(m, n, device=dev)
@@ -88,23 +95,26 @@ def main():
                 try:
                     t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128), 20 if m > 64 else 200, copies)
                 except RuntimeError as e:
-                    print(json.dumps({"shape": name, "M": m, "impl": label, "error": str(e)[:100]}))
+                    emit({"shape": name, "M": m, "impl": label, "error": str(e)[:100]})
                     continue
                 finally:
                     lib.sb200_gptq4_set_impl(0)
-                rec = {"shape": name, "K": k, "N": n, "M": m, "impl": label, "acts": "fp16->fp32" if os.environ.get("SB200_FP16_ACTS", "1") == "1" else "fp32", "us": t * 1e6, "TFLOPs": 2.0 * m * k * n / t / 1e12,
-                       "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9}
-                print(json.dumps(rec))
-                totals.setdefault((m, label), 0.0)
-                totals[(m, label)] += t * cnt * LAYERS
+                emit({"shape": name, "K": k, "N": n, "M": m, "impl": label, "acts": "fp16->fp32" if fp16_acts else "fp32",
+                      "us": t * 1e6, "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9})
+                totals[(m, label)] = totals.get((m, label), 0.0) + t * cnt * LAYERS
             if ref is not None:
                 reps = 4 if m > 64 else 200
                 t = timeit(lambda i: ref.vecgroupquant4matmul(x, ws[i % copies][0], y, ws[i % copies][1], ws[i % copies][2], 128), reps, copies)
-                print(json.dumps({"shape": name, "K": k, "N": n, "M": m, "impl": "reference_cuda", "us": t * 1e6,
-                                  "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9}))
-                totals.setdefault((m, "reference_cuda"), 0.0)
-                totals[(m, "reference_cuda")] += t * cnt * LAYERS
+                emit({"shape": name, "K": k, "N": n, "M": m, "impl": "reference_cuda", "us": t * 1e6,
+                      "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9})
+                totals[(m, "reference_cuda")] = totals.get((m, "reference_cuda"), 0.0) + t * cnt * LAYERS
             del ws
+    return totals
+
+
+def main():
+    ms = [int(a) for a in sys.argv[1:]] or [1, 16, 2048]
+    totals = run(ms)
     for (m, label), t in sorted(totals.items()):
         print(json.dumps({"summary": "llama7b_all_linears", "M": m, "impl": label, "ms_per_forward": t * 1e3, "tok_per_s": m / t}))
 

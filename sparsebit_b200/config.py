@@ -19,17 +19,21 @@ class Node(dict):
         self[k] = v
 
 
-def quantizer_config(qscheme, bit, target, observer="minmax", layout="NCHW", alpha=0.001, qtype="uniform", disable=False):
+def quantizer_config(qscheme, bit, target, observer="minmax", layout="NCHW", alpha=0.001, qtype="uniform", disable=False,
+                     pact_alpha=10, ema_ratio=0.9):
     """The ``config.W`` / ``config.A`` sub-tree + TARGET that ``build_quantizer`` receives
     (quant_model.py:97-137).  ``target``: "weight" | "feature"."""
     from .quantization.common import QuantTarget
 
     obs = {"TYPE": observer, "PERCENTILE": {"ALPHA": alpha}}
+    quantizer = {"TYPE": qtype, "DISABLE": disable, "BIT": bit}
     if target == "feature":
         obs["LAYOUT"] = layout
+        obs["MOVING_AVERAGE"] = {"EMA_RATIO": ema_ratio}   # quant_config.py:41-42
+        quantizer["PACT"] = {"ALPHA_VALUE": pact_alpha}    # quant_config.py:35-36
     return Node(
         QSCHEME=qscheme,
-        QUANTIZER={"TYPE": qtype, "DISABLE": disable, "BIT": bit},
+        QUANTIZER=quantizer,
         OBSERVER=obs,
         TARGET=(QuantTarget.WEIGHT if target == "weight" else QuantTarget.FEATURE,),
     )

@@ -42,7 +42,7 @@ class DataCache:
         self._batches += 1
         if self.qdesc.bs_axis is not None:
             self._batch_size += x.shape[self.qdesc.bs_axis]
-        if self._owner is None or self._owner.KEEP_DATA:
+        if self._owner is None or getattr(self._owner, "keep_data", self._owner.KEEP_DATA):
             self._tensors.append(x)
         if self._owner is not None:
             self._owner._ingest(x)
@@ -67,7 +67,7 @@ class DataCache:
     def rows(self, per_channel):
         """Cached batches as 2-D [rows, row_len] device views: one row per tensor (layer-wise) or
         one row per channel (channel-first; a transposing copy unless ch_axis == 0)."""
-        assert self._batches, "No data cached!"
+        assert self._batches and self._tensors, "No data cached!"
         ch = self.qdesc.ch_axis
         out = []
         for t in self._tensors:

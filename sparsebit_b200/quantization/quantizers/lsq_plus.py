@@ -1,0 +1,50 @@
+"""``TYPE = "lsq+"`` (sparsebit/quantization/quantizers/lsq_plus.py:14-82): LSQ with a learnable
+zero point for per-tensor-affine activations (initialised by the observer, lsq_plus.py:41-52) and a
+mean +- 3 std step-size initialisation for per-channel-symmetric weights (lsq_plus.py:24-40)."""
+import torch
+import torch.nn as nn
+
+from . import Quantizer as BaseQuantizer
+from . import register_quantizer
+from .lsq import GradScale, clamp_qparams, grad_scale_ratio
+from .quant_tensor import STE
+
+
+@register_quantizer
+class Quantizer(BaseQuantizer):
+    TYPE = "LSQ+"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.init_params = False
+        self.observer.keep_data = True  # the step-size initialisation needs the calibration batches themselves
+
+    def calc_qparams(self):
+        if self.fake_fused or self.init_params:
+            return self.scale, self.zero_point
+        qd = self.qdesc
+        if self.is_perchannel:
+            assert self.is_symmetric, "LSQ+ only support per-channel-symmetric quant for weight"
+            rows = torch.cat(self.observer.data_cache.rows(True), dim=1)
+            std, mean = torch.std_mean(rows, dim=1)  # unbiased, like Tensor.std
+            scale = 2 * torch.maximum((mean - 3 * std).abs(), (mean + 3 * std).abs()) / (qd.qmax - qd.qmin)
+            self.observer._reset()
+            self.scale = nn.Parameter(self._broadcast_qparams(scale.to(self.device)))
+            self.zero_point = self._broadcast_qparams(torch.zeros_like(self.scale.detach()))
+        else:
+            assert not self.is_symmetric, "LSQ+ only support per-tensor-affine quant for activation"
+            scale, zero_point = self.observer.calc_qparams()
+            self.scale = nn.Parameter(self._broadcast_qparams(scale.to(self.device)))
+            self.zero_point = nn.Parameter(self._broadcast_qparams(zero_point.clamp(qd.qmin, qd.qmax).to(self.device)))
+        self.init_params = True
+        return self.scale, self.zero_point
+
+    def _qparams_preprocess(self, x):
+        return clamp_qparams(self)
+
+    def _forward(self, x, scale, zero_point):
+        ratio = grad_scale_ratio(x, self.qdesc)
+        scale = GradScale.apply(scale, ratio)
+        if zero_point.requires_grad:
+            zero_point = GradScale.apply(zero_point, ratio)
+        return STE.apply(x, scale, zero_point, self.qdesc, self.backend)

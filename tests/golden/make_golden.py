@@ -228,9 +228,59 @@ def gen_gptq():
     save("gptq", **out)
 
 
+def gen_next_rows():
+    """SURVEY 8(f)#2 rows: LSQ / LSQ+ / PACT / DoReFa quantizers and the MovingAverage observer."""
+    g = torch.Generator().manual_seed(2024)
+    out = {}
+    cases = []
+    specs = [
+        # name, qtype, observer, scheme, bit, target, layout, shapes
+        ("lsq_pt_a4", "lsq", "minmax", "per-tensor-affine", 4, "feature", "NCHW", [(4, 3, 12, 12)] * 2),
+        ("lsq_pt_sym4", "lsq", "minmax", "per-tensor-symmetric", 4, "feature", "NCHW", [(4, 3, 12, 12)]),
+        ("lsq_pc_w4", "lsq", "minmax", "per-channel-symmetric", 4, "weight", None, [(8, 5, 3, 3)]),
+        ("lsqp_pt_a8", "lsq+", "minmax", "per-tensor-affine", 8, "feature", "NCHW", [(4, 3, 12, 12)] * 2),
+        ("lsqp_pc_w4", "lsq+", "minmax", "per-channel-symmetric", 4, "weight", None, [(8, 5, 3, 3)]),
+        ("pact_pt_a4", "pact", "minmax", "per-tensor-affine", 4, "feature", "NCHW", [(4, 3, 12, 12)]),
+        ("pact_pt_s8", "pact", "minmax", "per-tensor-symmetric", 8, "feature", "NCHW", [(4, 3, 12, 12)]),
+        ("dorefa_w4", "dorefa", "minmax", "per-tensor-symmetric", 4, "weight", None, [(8, 5, 3, 3)]),
+        ("mavg_pt", "uniform", "moving_average", "per-tensor-symmetric", 8, "feature", "NCHW", [(5, 3, 8, 8), (4, 3, 8, 8), (6, 3, 8, 8)]),
+        ("mavg_nlc", "uniform", "moving_average", "per-tensor-affine", 8, "feature", "NLC", [(3, 7, 16), (3, 7, 16)]),
+    ]
+    for name, qtype, obs, scheme, bit, target, layout, shapes in specs:
+        cfg = R.make_cfg(scheme, bit, target, obs, layout or "NCHW", qtype=qtype)
+        if target == "feature":
+            cfg.QUANTIZER.PACT = R._CfgNode({"ALPHA_VALUE": 3})
+            cfg.OBSERVER.MOVING_AVERAGE = R._CfgNode({"EMA_RATIO": 0.9})
+        q = build_quantizer(cfg)
+        q.set_backend(Backend.VIRTUAL)
+        xs = []
+        for i, shp in enumerate(shapes):
+            x = torch.randn(shp, generator=g) * (1.0 + 0.5 * i)
+            if "aff" in scheme and target == "feature" and qtype != "pact":
+                x = torch.relu(x)
+            xs.append(x)
+            q.update_observer(x)
+        with torch.no_grad():
+            scale, zp = q.calc_qparams()
+            q.enable_quant()
+            y = q(xs[0])
+            scale, zp = q._qparams_preprocess(xs[0]) if qtype in ("lsq", "lsq+", "pact") else (q.scale, q.zero_point)
+        cases.append(name)
+        for i, x in enumerate(xs):
+            out[f"{name}_x{i}"] = x.numpy()
+        out[name + "_nb"] = np.array(len(xs))
+        out[name + "_scale"] = scale.detach().reshape(-1).numpy()
+        out[name + "_zp"] = zp.detach().reshape(-1).numpy()
+        out[name + "_y"] = y.detach().numpy()
+        out[name + "_meta"] = np.array([q.qdesc.qmin, q.qdesc.qmax, q.qdesc.ch_axis, int(q.qdesc.is_perchannel), int(q.qdesc.is_symmetric), bit])
+    out["cases"] = np.array(cases)
+    save("next_rows", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     gen_qdq()
     gen_observers()
     gen_sparse()
     gen_gptq()
+    gen_next_rows()
