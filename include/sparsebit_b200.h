@@ -86,6 +86,13 @@ int sb200_qdq_stats_pertensor_fwd(const float* x, const float* scale, const floa
 int sb200_qdq_pertensor_fwd_host(const float* x_host, float scale, float zero_point,
                                  float* out_host, float* minmax_host, int64_t n, int qmin, int qmax,
                                  int rounding);
+/* Asynchronous form: enqueues the copies / kernels and returns; host buffers (pinned for real overlap)
+ * must stay valid and untouched until sb200_host_sync() returns.  Back-to-back calls keep the H2D and D2H
+ * engines busy across calls instead of draining the pipeline once per tensor. */
+int sb200_qdq_pertensor_fwd_host_async(const float* x_host, float scale, float zero_point,
+                                       float* out_host, float* minmax_host, int64_t n, int qmin,
+                                       int qmax, int rounding);
+int sb200_host_sync(void);
 int sb200_qdq_perchannel_fwd_host(const float* x_host, const float* scale_host,
                                   const float* zero_point_host, float* out_host, int64_t outer,
                                   int64_t channels, int64_t inner, int qmin, int qmax,

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "sb200_qdq_perchannel_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
     "sb200_qdq_stats_pertensor_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "sb200_qdq_pertensor_fwd_host": (c_int, [c_vp, c_f, c_f, c_vp, c_vp, c_i64, c_int, c_int, c_int]),
+    "sb200_qdq_pertensor_fwd_host_async": (c_int, [c_vp, c_f, c_f, c_vp, c_vp, c_i64, c_int, c_int, c_int]),
+    "sb200_host_sync": (c_int, []),
     "sb200_qdq_perchannel_fwd_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int]),
     "sb200_qdq_bwd_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "sb200_qdq_pertensor_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_sz, c_vp]),

@@ -40,3 +40,24 @@ def test_perchannel_host(shape):
     outer, inner = shape[0], int(np.prod(shape[2:]))
     _lib.check(lib.sb200_qdq_perchannel_fwd_host(x.data_ptr(), s.data_ptr(), z.data_ptr(), out.data_ptr(), outer, c, inner, -128, 127, 0))
     assert bits_equal(out.numpy(), oqdq.qdq(x.numpy(), s.numpy(), z.numpy(), -128, 127, 1))
+
+
+def test_async_host_calls_overlap_and_sync():
+    """Several asynchronous host-buffer calls in flight (more than the ring has slots), then one sync."""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    xs, outs, mms, exps = [], [], [], []
+    for i, n in enumerate([5_000_003, 1000, (4 << 20) * 3 + 7, 64, 9_999_999]):
+        x = torch.from_numpy((rng.standard_normal(n) * (1 + i)).astype(np.float32)).pin_memory()
+        out = torch.empty(n).pin_memory()
+        mm = (ctypes.c_float * 2)()
+        s = 0.01 * (i + 1)
+        _lib.check(lib.sb200_qdq_pertensor_fwd_host_async(x.data_ptr(), ctypes.c_float(s), ctypes.c_float(2.0), out.data_ptr(),
+                                                      ctypes.addressof(mm) if i % 2 == 0 else None, n, 0, 255, 0))
+        xs.append(x); outs.append(out); mms.append(mm)
+        exps.append(oqdq.qdq(x.numpy(), np.float32([s]), np.float32([2.0]), 0, 255))
+    _lib.check(lib.sb200_host_sync())
+    for i, (x, out, mm, exp) in enumerate(zip(xs, outs, mms, exps)):
+        assert bits_equal(out.numpy(), exp), i
+        if i % 2 == 0:
+            assert mm[0] == float(x.min()) and mm[1] == float(x.max())
