@@ -385,6 +385,23 @@ def main():
                 "kernel": "sb200::stream_kernel<MODE_TENSOR,VEC4,DOQ,STORE,STATS> (sb200_qdq_stats_pertensor_fwd)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
                 "kernel_share_of_step": act_ms / (ms_per_step * args.steps), "peak_source": peak_src}
+    # DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/): bytes the HBM actually
+    # moved during the captured launches relative to their algorithmic bytes, applied to this run's average launch.
+    try:
+        import re
+
+        txt = open(os.path.join(ROOT, "profiles", "r01_prof_qdq_stats.txt")).read()
+        rd = [float(v) for v in re.findall(r"dram__bytes_read\.sum\s+([0-9.]+) Mbyte", txt)]
+        wr = [float(v) for v in re.findall(r"dram__bytes_write\.sum\s+([0-9.]+) Mbyte", txt)]
+        if rd and len(rd) == len(wr):
+            # captured launches: sites 0..2 of the step ([256,3,224,224], 2 x [256,64,56,56]); algorithmic = 8 B/elem
+            alg = [a[0].numel() * 8 / 1e6 for a in acts[: len(rd)]]
+            ratio = (sum(rd) + sum(wr)) / sum(alg)
+            roofline["traffic"] = ratio * alg_bytes_per_launch
+            roofline["traffic_note"] = (f"dram__bytes_read+write / algorithmic = {ratio:.3f} over {len(rd)} captured launches "
+                                        "(reads == algorithmic; part of the writes is still in L2 when the kernel ends)")
+    except Exception:
+        pass
     # headline tensor alone: [256,3,224,224] (308 MB in+out > L2), 30 back-to-back launches
     a0 = (acts[0][0].data_ptr(), acts[0][2].data_ptr(), acts[0][3].data_ptr(), acts[0][1].data_ptr(), mm_states.data_ptr(),
           acts[0][0].numel(), 0, 255, 0, stream)
