@@ -20,12 +20,12 @@ class Node(dict):
 
 
 def quantizer_config(qscheme, bit, target, observer="minmax", layout="NCHW", alpha=0.001, qtype="uniform", disable=False,
-                     pact_alpha=10, ema_ratio=0.9):
+                     pact_alpha=10, ema_ratio=0.9, aciq_distribution="GAUS"):
     """The ``config.W`` / ``config.A`` sub-tree + TARGET that ``build_quantizer`` receives
     (quant_model.py:97-137).  ``target``: "weight" | "feature"."""
     from .quantization.common import QuantTarget
 
-    obs = {"TYPE": observer, "PERCENTILE": {"ALPHA": alpha}}
+    obs = {"TYPE": observer, "PERCENTILE": {"ALPHA": alpha}, "ACIQ": {"DISTRIBUTION": aciq_distribution}}
     quantizer = {"TYPE": qtype, "DISABLE": disable, "BIT": bit}
     if target == "feature":
         obs["LAYOUT"] = layout

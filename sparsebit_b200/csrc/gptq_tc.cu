@@ -29,7 +29,6 @@
 #include <cuda_fp16.h>
 
 #include <mutex>
-#include <unordered_map>
 
 #include "common.cuh"
 
@@ -352,7 +351,6 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const float zsub = 1024.f + z_cur;
       z_cur = z_next;
       const __half2 sub = __float2half2_rn(zsub);
-      const __half2 sub16 = __float2half2_rn(zsub);  // same value; the x16 lanes are rescaled by an exact FMA
       const __half2 k16 = __float2half2_rn(0.0625f);
 #pragma unroll
       for (int r = 0; r < kBlockK / 8; ++r) {
@@ -365,7 +363,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         const uint32_t v2 = (hi & 0x000F000Fu) | 0x64006400u;  // (n2, n6)
         const uint32_t v3 = (hi & 0x00F000F0u) | 0x64006400u;  // 1024 + 16 * (n3, n7)
         // (1024 + 16 q) * 1/16 = 64 + q exactly;  64 + q - (zsub - 960) = q - (zsub - 1024)
-        const __half2 off = __hsub2(sub16, __float2half2_rn(960.f));
+        const __half2 off = __hsub2(sub, __float2half2_rn(960.f));
         const __half2 h0 = __hsub2(*reinterpret_cast<const __half2*>(&v0), sub);
         const __half2 h1 = __hfma2(*reinterpret_cast<const __half2*>(&v1), k16, __hneg2(off));
         const __half2 h2 = __hsub2(*reinterpret_cast<const __half2*>(&v2), sub);

@@ -10,7 +10,7 @@ def register_observer(cls):
 
 
 from .base import DataCache, Observer  # noqa: E402,F401
-from . import kl_histogram, minmax, moving_average, mse, percentile  # noqa: E402,F401
+from . import aciq, kl_histogram, minmax, moving_average, mse, percentile  # noqa: E402,F401
 
 
 def build_observer(config, qdesc):

@@ -245,9 +245,19 @@ def gen_next_rows():
         ("dorefa_w4", "dorefa", "minmax", "per-tensor-symmetric", 4, "weight", None, [(8, 5, 3, 3)]),
         ("mavg_pt", "uniform", "moving_average", "per-tensor-symmetric", 8, "feature", "NCHW", [(5, 3, 8, 8), (4, 3, 8, 8), (6, 3, 8, 8)]),
         ("mavg_nlc", "uniform", "moving_average", "per-tensor-affine", 8, "feature", "NLC", [(3, 7, 16), (3, 7, 16)]),
+        ("aciqg_pt_s8", "uniform", "aciq:gaus", "per-tensor-symmetric", 8, "feature", "NCHW", [(4, 3, 12, 12)] * 2),
+        ("aciqg_pt_a4", "uniform", "aciq:gaus", "per-tensor-affine", 4, "feature", "NCHW", [(4, 3, 12, 12)] * 2),
+        ("aciqg_pc_w8", "uniform", "aciq:gaus", "per-channel-symmetric", 8, "weight", None, [(8, 5, 3, 3)]),
+        ("aciql_pt_s8", "uniform", "aciq:laplace", "per-tensor-symmetric", 8, "feature", "NCHW", [(4, 3, 12, 12)] * 2),
+        ("aciql_pc_w4", "uniform", "aciq:laplace", "per-channel-symmetric", 4, "weight", None, [(8, 5, 3, 3)]),
     ]
     for name, qtype, obs, scheme, bit, target, layout, shapes in specs:
+        dist_mode = None
+        if obs.startswith("aciq"):
+            obs, dist_mode = obs.split(":")
         cfg = R.make_cfg(scheme, bit, target, obs, layout or "NCHW", qtype=qtype)
+        if dist_mode:
+            cfg.OBSERVER.ACIQ = R._CfgNode({"DISTRIBUTION": dist_mode})
         if target == "feature":
             cfg.QUANTIZER.PACT = R._CfgNode({"ALPHA_VALUE": 3})
             cfg.OBSERVER.MOVING_AVERAGE = R._CfgNode({"EMA_RATIO": 0.9})

@@ -15,21 +15,23 @@ from sparsebit_b200.quantization.common import Backend
 
 pytestmark = pytest.mark.gpu
 SCHEMES = {(0, 1): "per-tensor-symmetric", (0, 0): "per-tensor-affine", (1, 1): "per-channel-symmetric", (1, 0): "per-channel-affine"}
-QTYPE = {"lsq": "lsq", "lsqp": "lsq+", "pact": "pact", "dorefa": "dorefa", "mavg": "uniform"}
+QTYPE = {"lsq": "lsq", "lsqp": "lsq+", "pact": "pact", "dorefa": "dorefa", "mavg": "uniform", "aciqg": "uniform", "aciql": "uniform"}
+OBSERVER = {"mavg": "moving_average", "aciqg": "aciq", "aciql": "aciq"}
 # scheme the reference was CONFIGURED with (LSQ may flip affine -> symmetric when it sees negatives)
 CONFIGURED = {"lsq_pt_a4": "per-tensor-affine", "lsq_pt_sym4": "per-tensor-symmetric", "lsq_pc_w4": "per-channel-symmetric",
               "lsqp_pt_a8": "per-tensor-affine", "lsqp_pc_w4": "per-channel-symmetric", "pact_pt_a4": "per-tensor-affine",
               "pact_pt_s8": "per-tensor-symmetric", "dorefa_w4": "per-tensor-symmetric", "mavg_pt": "per-tensor-symmetric",
-              "mavg_nlc": "per-tensor-affine"}
+              "mavg_nlc": "per-tensor-affine", "aciqg_pt_s8": "per-tensor-symmetric", "aciqg_pt_a4": "per-tensor-affine",
+              "aciqg_pc_w8": "per-channel-symmetric", "aciql_pt_s8": "per-tensor-symmetric", "aciql_pc_w4": "per-channel-symmetric"}
 
 
 def _build(g, name):
     qmin, qmax, ch_axis, perch, sym, bit = (int(v) for v in g[name + "_meta"])
     prefix = name.split("_")[0]
-    target = "weight" if name.endswith(("w4",)) else "feature"
+    target = "weight" if name.endswith(("w4", "w8")) else "feature"
     layout = "NLC" if ch_axis == 2 else "NCHW"
-    cfg = sbcfg.quantizer_config(CONFIGURED[name], bit, target, "moving_average" if prefix == "mavg" else "minmax", layout,
-                                 qtype=QTYPE[prefix], pact_alpha=3, ema_ratio=0.9)
+    cfg = sbcfg.quantizer_config(CONFIGURED[name], bit, target, OBSERVER.get(prefix, "minmax"), layout, qtype=QTYPE[prefix],
+                                 pact_alpha=3, ema_ratio=0.9, aciq_distribution="LAPLACE" if prefix == "aciql" else "GAUS")
     q = build_quantizer(cfg).to(dev())
     q.set_backend(Backend.VIRTUAL)
     xs = [g[f"{name}_x{i}"] for i in range(int(g[name + "_nb"]))]
@@ -53,7 +55,9 @@ def test_next_row_quantizers_match_reference(golden):
             # LSQ-type step sizes come from a float mean/std over the data: 2e-6 relative (summation order)
             np.testing.assert_allclose(scale.reshape(-1).cpu().numpy(), g[name + "_scale"], rtol=2e-6, err_msg=name)
             assert bits_equal(zp.reshape(-1).cpu().numpy(), g[name + "_zp"]), name
-            if prefix in ("lsq", "lsqp"):  # decouple the forward compare from the init reduction
+            if prefix in ("mavg", "aciqg", "pact"):  # min/max-derived qparams: bit-exact
+                assert bits_equal(scale.reshape(-1).cpu().numpy(), g[name + "_scale"]), name
+            if prefix in ("lsq", "lsqp", "aciql"):  # decouple the forward compare from the float reduction
                 q.scale.data.copy_(t(g[name + "_scale"]).reshape(q.scale.shape))
             y = q(t(xs[0])).cpu().numpy()
         if prefix == "dorefa":  # tanh runs in torch (CUDA vs CPU libm may differ by an ulp -> rare grid flips)
