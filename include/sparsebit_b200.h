@@ -204,6 +204,27 @@ int sb200_mask_apply_qdq_perchannel(const float* w, const uint8_t* mask, const f
                                     int64_t channels, int64_t inner, int qmin, int qmax,
                                     int rounding, void* stream);
 
+/* ---- (3b) AdaRound weight quantizer (sparsebit/quantization/quantizers/adaround.py) -------
+ * The one quantizer that bypasses STE.  [outer, channels, inner] geometry as above (per-tensor:
+ * 1, 1, n); scale / zero_point hold `channels` floats; v has the shape of x.
+ *   x_floor = floor(x / scale);  h(v) = clamp(sigmoid(v) * 1.2 - 0.1, 0, 1)
+ *   soft = 1 (training, adaround.py:48-49):  x_q = x_floor + h(v)
+ *   soft = 0 (eval,     adaround.py:50-51):  x_q = x_floor + (v >= 0)          -- exact
+ *   out = (clamp(x_q + zero_point, qmin, qmax) - zero_point) * scale           (adaround.py:52-53)
+ * zero_point is used as stored (not rounded), like the reference. */
+int sb200_adaround_fwd(const float* x, const float* v, const float* scale, const float* zero_point,
+                       float* out, int64_t outer, int64_t channels, int64_t inner, int qmin,
+                       int qmax, int soft, void* stream);
+/* grad_v = d out / d v * grad_y for soft = 1 (what autograd derives from adaround.py:40-54; x and
+ * scale receive no gradient: floor() has none and scale is a buffer). */
+int sb200_adaround_bwd(const float* x, const float* v, const float* scale, const float* zero_point,
+                       const float* grad_y, float* grad_v, int64_t outer, int64_t channels,
+                       int64_t inner, int qmin, int qmax, void* stream);
+/* v = -log(1.2 / (x/scale - floor(x/scale) + 0.1) - 1), so that h(v) = frac(x/scale)
+ * (init_variables, adaround.py:26-32). */
+int sb200_adaround_init(const float* x, const float* scale, float* v, int64_t outer,
+                        int64_t channels, int64_t inner, void* stream);
+
 /* ---- (4) GPTQ int4 group-wise dequant-matmul --------------------------------------------
  * Replaces cuda_kernel.vecquant4matmul / vecgroupquant4matmul
  * (large_language_models/llama/quantization/cuda/cuda_kernel.cpp:10-23,70,73;

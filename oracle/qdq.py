@@ -89,3 +89,59 @@ def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0
         return gx, np.array([gs_e.sum()]), np.array([gz_e.sum()])
     axes = tuple(a for a in range(x.ndim) if a != ch_axis)
     return gx, gs_e.sum(axis=axes), gz_e.sum(axis=axes)
+
+
+# --------------------------------------------------------------------------------------------
+# AdaRound (sparsebit/quantization/quantizers/adaround.py) -- the quantizer that bypasses STE.
+_STRETCH = F32(1.1 - (-0.1))  # zeta - gamma in Python doubles, narrowed to the tensor dtype by ATen
+_GAMMA = F32(-0.1)
+
+
+def _sigmoid(v):
+    with np.errstate(all="ignore"):
+        return (F32(1) / (F32(1) + np.exp(-np.asarray(v, F32)).astype(F32))).astype(F32)
+
+
+def adaround_soft_values(v):
+    """_get_soft_round_values, adaround.py:40-43: clamp(sigmoid(v) * (zeta - gamma) + gamma, 0, 1)."""
+    raw = ((_sigmoid(v) * _STRETCH).astype(F32) + _GAMMA).astype(F32)
+    return _clamp_keep_nan(raw, 0, 1), raw
+
+
+def adaround_forward(x, v, scale, zero_point, qmin, qmax, ch_axis=0, soft=False):
+    """_forward, adaround.py:46-54: x_floor = floor(x / scale); + soft values (training) or (v >= 0)
+    (eval); clamp(. + zp, qmin, qmax); (. - zp) * scale.  zero_point is NOT rounded here."""
+    x = np.asarray(x, F32)
+    s, zp = _bcast(scale, x, ch_axis), _bcast(zero_point, x, ch_axis)
+    with np.errstate(all="ignore"):
+        fl = np.floor((x / s).astype(F32))
+        r = adaround_soft_values(v)[0] if soft else (np.asarray(v, F32) >= 0).astype(F32)
+        xq = _clamp_keep_nan(((fl + r).astype(F32) + zp).astype(F32), qmin, qmax)
+        return ((xq - zp).astype(F32) * s).astype(F32)
+
+
+def adaround_grad_v(x, v, scale, zero_point, grad_y, qmin, qmax, ch_axis=0):
+    """What autograd derives for d(sum(out * grad_y)) / dv in the training branch (fp64 restatement:
+    clamp passes gradients on the closed interval, sigmoid' = y (1 - y))."""
+    x = np.asarray(x, F32)
+    s, zp = _bcast(scale, x, ch_axis), _bcast(zero_point, x, ch_axis)
+    with np.errstate(all="ignore"):
+        fl = np.floor((x / s).astype(F32))
+        soft, raw = adaround_soft_values(v)
+        q = ((fl + soft).astype(F32) + zp).astype(F32)
+        live = (q >= F32(qmin)) & (q <= F32(qmax)) & (raw >= 0) & (raw <= 1)
+        y = _sigmoid(v).astype(np.float64)
+        g = np.asarray(grad_y, np.float64) * s.astype(np.float64) * float(_STRETCH) * y * (1 - y)
+        return np.where(live, g, 0.0)
+
+
+def adaround_init(x, scale, ch_axis=0):
+    """init_variables, adaround.py:26-32: v = -log((zeta - gamma) / (rest - gamma) - 1) with
+    rest = x/scale - floor(x/scale); ATen computes scalar / tensor as reciprocal(tensor) * scalar."""
+    x = np.asarray(x, F32)
+    s = _bcast(scale, x, ch_axis)
+    with np.errstate(all="ignore"):
+        qv = (x / s).astype(F32)
+        rest = (qv - np.floor(qv)).astype(F32)
+        ratio = ((F32(1) / (rest - _GAMMA).astype(F32)).astype(F32) * _STRETCH).astype(F32)
+        return (-np.log((ratio - F32(1)).astype(F32))).astype(F32)

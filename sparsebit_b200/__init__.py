@@ -31,8 +31,13 @@ def install():
     ref_obs = importlib.import_module("sparsebit.quantization.observers")
     from .quantization import observers as my_obs
 
-    for name in ("minmax", "mse", "percentile", "kl_histogram"):
+    for name in ("minmax", "mse", "percentile", "kl_histogram", "moving_average", "aciq"):
         ref_obs.OBSERVERS_MAP[name] = my_obs.OBSERVERS_MAP[name]
+    # QuantModel.prepare_calibration imports CalibrationRunner at call time (quant_model.py:185-189)
+    ref_cal = importlib.import_module("sparsebit.quantization.tools.calibration")
+    from .quantization.tools import CalibrationRunner
+
+    ref_cal.CalibrationRunner = CalibrationRunner
     try:
         ref_sp = importlib.import_module("sparsebit.sparse.sparsers")
         from .sparse import sparsers as my_sp

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "sb200_mask_apply": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply_qdq_perchannel": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
+    "sb200_adaround_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
+    "sb200_adaround_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp]),
+    "sb200_adaround_init": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "sb200_gptq4_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "sb200_gptq4_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_set_impl": (c_int, [c_int]),

@@ -107,6 +107,55 @@ def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, roundin
     return gx, gs, gzp
 
 
+# ----------------------------------------------------------------------------- AdaRound
+def _adaround_geometry(x, scale, ch_axis):
+    if ch_axis is None:
+        outer, c, inner = 1, 1, x.numel()
+    else:
+        outer, c, inner = channel_geometry(x.shape, ch_axis)
+    if scale.numel() != c:
+        raise SparsebitB200Error(f"adaround: qparams need {c} elements (got {scale.numel()})")
+    return outer, c, inner
+
+
+def adaround_forward(x, v, scale, zero_point, qmin, qmax, ch_axis=None, soft=False, out=None):
+    """adaround.py:46-54; soft=True is the training branch, soft=False the (exact) eval branch."""
+    lib = _lib.load()
+    _req(x, "data"), _req(v, "v"), _req(scale, "scale"), _req(zero_point, "zero_point")
+    if v.shape != x.shape:
+        raise SparsebitB200Error("adaround: v must have the shape of data")
+    outer, c, inner = _adaround_geometry(x, scale, ch_axis)
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        check(lib.sb200_adaround_fwd(x.data_ptr(), v.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), out.data_ptr(),
+                                     outer, c, inner, int(qmin), int(qmax), int(bool(soft)), _stream(x)))
+    return out
+
+
+def adaround_backward(x, v, scale, zero_point, grad_y, qmin, qmax, ch_axis=None):
+    lib = _lib.load()
+    _req(x, "data"), _req(v, "v"), _req(scale, "scale"), _req(zero_point, "zero_point"), _req(grad_y, "grad")
+    if v.shape != x.shape or grad_y.shape != x.shape:
+        raise SparsebitB200Error("adaround: v and grad_y must have the shape of data")
+    outer, c, inner = _adaround_geometry(x, scale, ch_axis)
+    gv = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.sb200_adaround_bwd(x.data_ptr(), v.data_ptr(), scale.data_ptr(), zero_point.data_ptr(),
+                                     grad_y.data_ptr(), gv.data_ptr(), outer, c, inner, int(qmin), int(qmax), _stream(x)))
+    return gv
+
+
+def adaround_init(x, scale, ch_axis=None):
+    """adaround.py:26-32."""
+    lib = _lib.load()
+    _req(x, "data"), _req(scale, "scale")
+    outer, c, inner = _adaround_geometry(x, scale, ch_axis)
+    v = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.sb200_adaround_init(x.data_ptr(), scale.data_ptr(), v.data_ptr(), outer, c, inner, _stream(x)))
+    return v
+
+
 # ----------------------------------------------------------------------------- MinMax
 def minmax_new(channels, device):
     """Fresh running min/max state: int32[2*C] (bit pattern of the uint32 ordered keys)."""

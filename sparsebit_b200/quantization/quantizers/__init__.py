@@ -10,7 +10,7 @@ def register_quantizer(cls):
 
 
 from .base import Quantizer  # noqa: E402,F401
-from . import dorefa, lsq, lsq_plus, pact, uniform  # noqa: E402,F401
+from . import adaround, dorefa, lsq, lsq_plus, pact, uniform  # noqa: E402,F401
 
 
 def build_quantizer(cfg):

@@ -1,0 +1,220 @@
+"""Device-resident, streaming CalibrationRunner.
+
+Same driver contract as sparsebit/quantization/tools/calibration.py:11-160
+(``prepare_calibration()`` -> run the calibration batches through the model -> ``layerwise_calibration``)
+and the same resulting qparams, but:
+
+* the reference records the model inputs on the CPU, then replays the graph node by node, moving every
+  activation of every batch host <-> device and caching it in full (calibration.py:38,137-160;
+  observers/base.py:12-36).  Here the observers are fed *during* the calibration forwards by
+  forward-pre-hooks: the streaming observers fold each batch into device-side running statistics
+  (min/max keys, histograms, counts), so nothing is cached for MinMax / MovingAverage / ACIQ-gaus / KL
+  and nothing ever leaves HBM;
+* the layer-wise replay is kept for the two cases that need per-layer tensors -- AdaRound
+  reconstruction and ``asym=True`` -- with the per-node storage held on the device and released as soon
+  as a node's last user has run.
+
+Under ``sparsebit_b200.distributed.enable(group)`` every rank streams its shard of the calibration set and
+the observers all-reduce their statistics inside ``calc_qparams`` -- the runner itself has no collective.
+"""
+import torch
+import torch.fx as fx
+
+
+def _is_quant_opr(module):
+    return isinstance(module, torch.nn.Module) and hasattr(module, "input_quantizer") and hasattr(module, "weight_quantizer")
+
+
+def _live(quantizer):
+    return quantizer is not None and not quantizer.fake_fused
+
+
+def trace_quant_model(model):
+    """``torch.fx`` trace that keeps every quant operator a leaf (the role of the reference's QTracer,
+    tools/graph_wrapper.py) -- needed only for the layer-wise replay."""
+
+    class _Tracer(fx.Tracer):
+        def is_leaf_module(self, m, qualname):
+            return _is_quant_opr(m) or super().is_leaf_module(m, qualname)
+
+    graph = _Tracer().trace(model)
+    return fx.GraphModule(model, graph)
+
+
+def _tensors_of(args):
+    """Flattened tensor leaves of (nested) positional arguments, in order (calibration.py:24-31)."""
+    out = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            out.append(a)
+        elif isinstance(a, (list, tuple)):
+            out.extend(_tensors_of(a))
+    return out
+
+
+class CalibrationRunner:
+    def __init__(self, model, streaming=True, record_inputs=None):
+        """``model``: an ``nn.Module`` whose quant operators expose ``input_quantizer`` /
+        ``weight_quantizer`` / ``set_quant`` (a ``torch.fx.GraphModule`` for the layer-wise replay).
+        ``streaming=False`` forces the replay for every configuration.  ``record_inputs`` (default:
+        only when the model is a GraphModule) keeps references to the calibration inputs -- on the
+        device, no copy -- so that ``layerwise_calibration`` may still choose the replay."""
+        self.model = model
+        self.streaming = streaming
+        self.is_graph = isinstance(model, fx.GraphModule)
+        self.record_inputs = self.is_graph if record_inputs is None else record_inputs
+        assert streaming or self.is_graph, "the layer-wise replay needs a torch.fx.GraphModule (trace_quant_model)"
+        self._handles = []
+        self._inputs = []     # one tuple of positional inputs per calibration batch
+        self._order = []      # quant operators in first-execution order
+        self._seen = set()
+
+    # ------------------------------------------------------------------ pass 1: streaming hooks
+    def prepare_calibration(self):
+        self.model.eval()  # the reference's replay runs every operator in eval mode (calibration.py:141-142)
+        seen = set()
+        for module in self.model.modules():
+            if _is_quant_opr(module) and id(module) not in seen:
+                seen.add(id(module))
+                self._handles.append(module.register_forward_pre_hook(self._feed_observer))
+        if self.record_inputs:
+            self._handles.append(self.model.register_forward_pre_hook(self._record))
+        self.builder = self  # the reference asserts on this attribute (calibration.py:72)
+
+    def _record(self, module, args):
+        self._inputs.append(tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in args))
+
+    def _feed_observer(self, module, args):
+        if id(module) not in self._seen:
+            self._seen.add(id(module))
+            self._order.append(module)
+        if self.streaming and _live(module.input_quantizer):
+            for x in _tensors_of(args):
+                module.input_quantizer.update_observer(x.detach())
+
+    def _remove_hooks(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    # ------------------------------------------------------------------ pass 2: qparams
+    def layerwise_calibration(self, device=None, asym=False, w_quant=False, a_quant=False):
+        """calibration.py:64-98.  ``device`` is accepted for signature parity; tensors stay where the
+        calibration forwards produced them."""
+        assert hasattr(self, "builder"), "run self.prepare_calibration first!"
+        self._remove_hooks()
+        wants_replay = asym or any(
+            m.weight_quantizer is not None and m.weight_quantizer.TYPE.lower() == "adaround" for m in self._quant_oprs())
+        if self.streaming and not wants_replay:
+            self._finish_streaming()
+        else:
+            assert self.is_graph and self._inputs, "AdaRound / asym calibration replays the graph: pass a GraphModule"
+            if self.streaming:  # statistics gathered in pass 1 are recomputed per layer
+                for m in self._quant_oprs():
+                    if _live(m.input_quantizer):
+                        m.input_quantizer.observer.data_cache.reset()
+            self._replay(asym, w_quant, a_quant)
+        self._inputs = []
+
+    def _quant_oprs(self):
+        if self._order:
+            return list(self._order)
+        return [m for m in self.model.modules() if _is_quant_opr(m)]
+
+    def _finish_streaming(self):
+        for module in self._quant_oprs():
+            if _live(module.input_quantizer):
+                module.input_quantizer.calc_qparams()
+                module.input_quantizer.observer.data_cache.reset()
+            self._calibrate_weight(module)
+
+    @staticmethod
+    def _calibrate_weight(module):
+        wq = module.weight_quantizer
+        if wq is None:
+            return
+        wq.update_observer(module.weight)
+        wq.calc_qparams()
+
+    # ------------------------------------------------------------------ layer-wise replay (device resident)
+    def _replay(self, asym, w_quant, a_quant):
+        from ..quantizers.adaround import reconstruct_qlayer
+
+        graph = self.model.graph
+        n_batches = len(self._inputs)
+        placeholders = [n for n in graph.nodes if n.op == "placeholder"]
+        float_env, quant_env = {}, {}
+        pending = {n: len(n.users) for n in graph.nodes}
+
+        def release(node):
+            for inp in node.all_input_nodes:
+                pending[inp] -= 1
+                if pending[inp] == 0:
+                    float_env.pop(inp, None)
+                    quant_env.pop(inp, None)
+
+        for node in graph.nodes:
+            if node.op == "placeholder":
+                pos = placeholders.index(node)
+                float_env[node] = [batch[pos] for batch in self._inputs]
+                if asym:
+                    quant_env[node] = float_env[node]
+                continue
+            if node.op == "output":
+                continue
+            module = self.model.get_submodule(node.target) if node.op == "call_module" else None
+            quant_opr = module if _is_quant_opr(module) else None
+            # input quantizer: always on the float activations (calibration.py:100-115)
+            if quant_opr is not None and _live(quant_opr.input_quantizer):
+                for inp in node.all_input_nodes:
+                    for x in float_env[inp]:
+                        if isinstance(x, torch.Tensor):
+                            quant_opr.input_quantizer.update_observer(x)
+                quant_opr.input_quantizer.calc_qparams()
+                quant_opr.input_quantizer.observer.data_cache.reset()
+            float_env[node] = self._run_node(node, module, float_env, n_batches)
+            if quant_opr is not None:
+                quant_opr.set_quant(w_quant=False, a_quant=False)
+            if quant_opr is not None and quant_opr.weight_quantizer is not None:
+                self._calibrate_weight(quant_opr)
+                if quant_opr.weight_quantizer.TYPE.lower() == "adaround":
+                    assert len(node.all_input_nodes) == 1, "AdaRound not supports the oprs which has more than one inputs"
+                    source = quant_env if asym else float_env
+                    reconstruct_qlayer(quant_opr, torch.cat(source[node.all_input_nodes[0]], dim=0),
+                                       torch.cat(float_env[node], dim=0), a_quant=a_quant,
+                                       **getattr(self, "adaround_kwargs", {}))
+            if asym:
+                if quant_opr is not None:
+                    quant_opr.set_quant(w_quant, a_quant)
+                quant_env[node] = self._run_node(node, module, quant_env, n_batches)
+                if quant_opr is not None:
+                    quant_opr.set_quant(w_quant=False, a_quant=False)
+            release(node)
+
+    def _run_node(self, node, module, env, n_batches):
+        if node.op == "call_module":
+            module.eval()
+        outs = []
+        with torch.no_grad():
+            for b in range(n_batches):
+                if node.op == "get_attr":
+                    outs.append(_fetch_attr(self.model, node.target))
+                    continue
+                args = fx.node.map_arg(node.args, lambda n: env[n][b])
+                kwargs = fx.node.map_arg(node.kwargs, lambda n: env[n][b])
+                if node.op == "call_module":
+                    outs.append(module(*args, **kwargs))
+                elif node.op == "call_function":
+                    outs.append(node.target(*args, **kwargs))
+                elif node.op == "call_method":
+                    outs.append(getattr(args[0], node.target)(*args[1:], **kwargs))
+                else:
+                    raise NotImplementedError(node.op)
+        return outs
+
+
+def _fetch_attr(root, target):
+    obj = root
+    for part in target.split("."):
+        obj = getattr(obj, part)
+    return obj

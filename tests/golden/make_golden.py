@@ -284,7 +284,110 @@ def gen_next_rows():
         out[name + "_y"] = y.detach().numpy()
         out[name + "_meta"] = np.array([q.qdesc.qmin, q.qdesc.qmax, q.qdesc.ch_axis, int(q.qdesc.is_perchannel), int(q.qdesc.is_symmetric), bit])
     out["cases"] = np.array(cases)
+    # AdaRound (adaround.py): init_variables, eval (hard) and training (soft) forward, dL/dv by autograd
+    ada = []
+    for name, scheme, bit, shape in [("ada_pc_w4", "per-channel-symmetric", 4, (8, 5, 3, 3)),
+                                     ("ada_pc_w8", "per-channel-symmetric", 8, (6, 16)),
+                                     ("ada_pt_w4", "per-tensor-symmetric", 4, (8, 5, 3, 3)),
+                                     ("ada_pt_a3", "per-tensor-affine", 3, (7, 9))]:
+        cfg = R.make_cfg(scheme, bit, "weight", "minmax", "NCHW", qtype="adaround")
+        q = build_quantizer(cfg)
+        q.set_backend(Backend.VIRTUAL)
+        w = torch.randn(shape, generator=g) * 0.2
+        q.update_observer(w)
+        q.calc_qparams()
+        q.enable_quant()
+        q.init_variables(w)
+        v0 = q.v.detach().clone()
+        v1 = (v0 + torch.randn(shape, generator=g) * 2.0).clone()
+        q.v = torch.nn.Parameter(v1.clone())
+        q.eval()
+        with torch.no_grad():
+            y_hard = q(w)
+        q.train()
+        y_soft = q(w)
+        gy = torch.randn(shape, generator=g)
+        (y_soft * gy).sum().backward()
+        ada.append(name)
+        out[name + "_w"] = w.numpy()
+        out[name + "_v0"] = v0.numpy()
+        out[name + "_v1"] = v1.numpy()
+        out[name + "_scale"] = q.scale.detach().reshape(-1).numpy()
+        out[name + "_zp"] = q.zero_point.detach().reshape(-1).numpy()
+        out[name + "_yhard"] = y_hard.numpy()
+        out[name + "_ysoft"] = y_soft.detach().numpy()
+        out[name + "_gy"] = gy.numpy()
+        out[name + "_gv"] = q.v.grad.numpy()
+        out[name + "_meta"] = np.array([q.qdesc.qmin, q.qdesc.qmax, q.qdesc.ch_axis, int(q.qdesc.is_perchannel), int(q.qdesc.is_symmetric), bit])
+    out["ada_cases"] = np.array(ada)
     save("next_rows", **out)
+
+
+def gen_calibration():
+    """the reference's QuantModel + CalibrationRunner (tools/calibration.py) on a tiny CNN,
+    CPU.  Records the weights, the calibration batches and every quantizer's resulting qparams."""
+    import torch.nn as nn
+    from sparsebit.quantization import QuantModel
+    from sparsebit.quantization.quant_config import _C
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(3, 8, 3, padding=1)
+            self.relu1 = nn.ReLU()
+            self.conv2 = nn.Conv2d(8, 8, 3, stride=2)
+            self.relu2 = nn.ReLU()
+            self.fc = nn.Linear(8 * 3 * 3, 10)
+
+        def forward(self, x):
+            x = self.relu1(self.conv1(x))
+            x = self.relu2(self.conv2(x))
+            return self.fc(torch.flatten(x, 1))
+
+    torch.manual_seed(7)
+    net = Tiny().eval()
+    g = torch.Generator().manual_seed(77)
+    xs = [torch.randn(4, 3, 8, 8, generator=g) for _ in range(3)]
+    out = {"nb": np.array(len(xs))}
+    for k, v in net.state_dict().items():
+        out["sd_" + k] = v.numpy()
+    for i, x in enumerate(xs):
+        out[f"x{i}"] = x.numpy()
+    cases = []
+    for name, wscheme, wbit, wobs, ascheme, abit, aobs in [
+        ("mm8", "per-channel-symmetric", 8, "minmax", "per-tensor-affine", 8, "minmax"),
+        ("pct", "per-channel-symmetric", 4, "minmax", "per-tensor-symmetric", 8, "percentile"),
+        ("mse", "per-tensor-symmetric", 8, "mse", "per-tensor-affine", 4, "mse"),
+        ("mavg", "per-channel-symmetric", 8, "minmax", "per-tensor-affine", 8, "moving_average"),
+    ]:
+        cfg = _C.clone()
+        cfg.DEVICE = "cpu"
+        cfg.W.QSCHEME, cfg.W.QUANTIZER.BIT, cfg.W.OBSERVER.TYPE = wscheme, wbit, wobs
+        cfg.A.QSCHEME, cfg.A.QUANTIZER.BIT, cfg.A.OBSERVER.TYPE = ascheme, abit, aobs
+        import copy
+
+        qm = QuantModel(copy.deepcopy(net), cfg)
+        qm.prepare_calibration()
+        with torch.no_grad():
+            for x in xs:
+                qm(x)
+        qm.calc_qparams()
+        qm.set_quant(w_quant=True, a_quant=True)
+        with torch.no_grad():
+            y = qm(xs[0])
+        cases.append(name)
+        out[name + "_cfg"] = np.array([wscheme, str(wbit), wobs, ascheme, str(abit), aobs])
+        for mod in ("conv1", "conv2", "fc"):
+            m = getattr(qm.model, mod)
+            out[f"{name}_{mod}_as"] = m.input_quantizer.scale.reshape(-1).numpy()
+            out[f"{name}_{mod}_az"] = m.input_quantizer.zero_point.reshape(-1).numpy()
+            out[f"{name}_{mod}_ws"] = m.weight_quantizer.scale.reshape(-1).numpy()
+            out[f"{name}_{mod}_wz"] = m.weight_quantizer.zero_point.reshape(-1).numpy()
+        for mod in ("relu1", "relu2"):  # fused away by DISABLE_UNNECESSARY_QUANT
+            assert getattr(qm.model, mod).input_quantizer.fake_fused
+        out[name + "_y"] = y.numpy()
+    out["cases"] = np.array(cases)
+    save("calibration", **out)
 
 
 if __name__ == "__main__":
@@ -294,3 +397,4 @@ if __name__ == "__main__":
     gen_sparse()
     gen_gptq()
     gen_next_rows()
+    gen_calibration()

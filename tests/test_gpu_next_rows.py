@@ -85,3 +85,100 @@ def test_lsq_scale_gradient_uses_kernel_gs():
     sign = np.sign(q.scale.detach().reshape(-1).cpu().numpy())  # d|s|/ds
     np.testing.assert_allclose(q.scale.grad.reshape(-1).cpu().numpy(), egs * ratio * sign, rtol=1e-5)
     assert bits_equal(xr.grad.cpu().numpy(), egx)
+
+
+def _ada_quantizer(g, name):
+    qmin, qmax, ch_axis, perch, sym, bit = (int(v) for v in g[name + "_meta"])
+    q = build_quantizer(sbcfg.quantizer_config(SCHEMES[(perch, sym)], bit, "weight", qtype="adaround")).to(dev())
+    q.set_backend(Backend.VIRTUAL)
+    w = t(g[name + "_w"])
+    q.update_observer(w)
+    q.calc_qparams()
+    q.enable_quant()
+    return q, w
+
+
+def test_adaround_matches_reference(golden):
+    """AdaRound (adaround.py:26-54) through the plugin class: qparams and the eval branch bit-exact,
+    init / soft branch / dL/dv within 1e-5 relative (expf / logf vs the CPU libm)."""
+    g = golden("next_rows")
+    for name in g["ada_cases"]:
+        q, w = _ada_quantizer(g, name)
+        assert bits_equal(q.scale.reshape(-1).cpu().numpy(), g[name + "_scale"]), name
+        assert bits_equal(q.zero_point.reshape(-1).cpu().numpy(), g[name + "_zp"]), name
+        q.init_variables(w)
+        assert isinstance(q.v, torch.nn.Parameter) and q.v.shape == w.shape
+        np.testing.assert_allclose(q.v.detach().cpu().numpy(), g[name + "_v0"], rtol=1e-5, atol=1e-6, err_msg=name)
+        q.v = torch.nn.Parameter(t(g[name + "_v1"]))
+        q.eval()
+        with torch.no_grad():
+            assert bits_equal(q(w).cpu().numpy(), g[name + "_yhard"]), name
+        q.train()
+        y = q(w)
+        np.testing.assert_allclose(y.detach().cpu().numpy(), g[name + "_ysoft"], rtol=1e-5, atol=1e-7, err_msg=name)
+        (y * t(g[name + "_gy"])).sum().backward()
+        np.testing.assert_allclose(q.v.grad.cpu().numpy(), g[name + "_gv"], rtol=1e-5, atol=1e-8, err_msg=name)
+        # the differentiable regulariser input equals the oracle restatement
+        np.testing.assert_allclose(q._get_soft_round_values().detach().cpu().numpy(),
+                                   oqdq.adaround_soft_values(g[name + "_v1"])[0], rtol=1e-5, atol=1e-7)
+
+
+def test_adaround_kernels_vs_oracle_ragged():
+    """Odd inner sizes (scalar path), large per-tensor tensors (float4 path), NaN / inf inputs."""
+    from sparsebit_b200 import ops
+
+    rng = np.random.default_rng(7)
+    for shape, ch_axis in [((5, 7, 3), 0), ((3, 4, 1031), 1), ((1 << 18,), None), ((64, 147), 0), ((2, 2048, 9), 1)]:
+        x = (rng.standard_normal(shape) * 0.3).astype(np.float32)
+        v = (rng.standard_normal(shape) * 3).astype(np.float32)
+        c = 1 if ch_axis is None else shape[ch_axis]
+        s = (rng.uniform(0.01, 0.05, c)).astype(np.float32)
+        zp = np.rint(rng.uniform(-3, 3, c)).astype(np.float32)
+        if x.size > 100:
+            x.reshape(-1)[3], x.reshape(-1)[17], v.reshape(-1)[29] = np.nan, np.inf, np.nan
+        ax = 0 if ch_axis is None else ch_axis
+        hard = ops.adaround_forward(t(x), t(v), t(s), t(zp), -8, 7, ch_axis, soft=False).cpu().numpy()
+        assert bits_equal(hard, oqdq.adaround_forward(x, v, s, zp, -8, 7, ax, soft=False)), shape
+        soft = ops.adaround_forward(t(x), t(v), t(s), t(zp), -8, 7, ch_axis, soft=True).cpu().numpy()
+        np.testing.assert_allclose(soft, oqdq.adaround_forward(x, v, s, zp, -8, 7, ax, soft=True), rtol=1e-5, atol=1e-7)
+        gy = rng.standard_normal(shape).astype(np.float32)
+        ok = np.isfinite(x) & np.isfinite(v)
+        gv = ops.adaround_backward(t(x), t(v), t(s), t(zp), t(gy), -8, 7, ch_axis).cpu().numpy()
+        np.testing.assert_allclose(gv[ok], oqdq.adaround_grad_v(x, v, s, zp, gy, -8, 7, ax)[ok], rtol=1e-5, atol=1e-8)
+        v0 = ops.adaround_init(t(x), t(s), ch_axis).cpu().numpy()
+        np.testing.assert_allclose(v0[ok], oqdq.adaround_init(x, s, ax)[ok], rtol=1e-5, atol=1e-6)
+
+
+def test_adaround_reconstruct_qlayer_reduces_error():
+    """reconstruct_qlayer (adaround.py:57-110) on a tiny linear layer: the learned rounding must not be
+    worse than round-to-nearest on the layer's outputs, and every v must have left the soft zone."""
+    from sparsebit_b200.quantization.quantizers.adaround import reconstruct_qlayer
+
+    class QLinear(torch.nn.Module):  # the slice of QuantOpr the routine uses (modules/base.py:48-66)
+        def __init__(self, lin, wq):
+            super().__init__()
+            self.weight, self.bias, self.weight_quantizer = lin.weight, lin.bias, wq
+
+        def set_quant(self, w_quant=False, a_quant=False):
+            self.weight_quantizer.enable_quant() if w_quant else self.weight_quantizer.disable_quant()
+
+        def forward(self, x):
+            return torch.nn.functional.linear(x, self.weight_quantizer(self.weight), self.bias)
+
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(32, 16).to(dev())
+    wq = build_quantizer(sbcfg.quantizer_config("per-channel-symmetric", 3, "weight", qtype="adaround")).to(dev())
+    wq.set_backend(Backend.VIRTUAL)
+    wq.update_observer(lin.weight)
+    wq.calc_qparams()
+    layer = QLinear(lin, wq)
+    x = torch.randn(256, 32, device=dev())
+    with torch.no_grad():
+        ref = lin(x)
+        nearest = torch.nn.functional.linear(x, torch.round(lin.weight / wq.scale).clamp(-4, 3) * wq.scale, lin.bias)
+        err_nearest = (nearest - ref).pow(2).mean().item()
+    reconstruct_qlayer(layer, x, ref, batch_size=64, max_steps=600, print_freq=0)
+    assert not wq.training
+    with torch.no_grad():
+        err_ada = (layer(x) - ref).pow(2).mean().item()
+    assert err_ada <= err_nearest * 1.02, (err_ada, err_nearest)

@@ -120,3 +120,84 @@ def test_quantizer_state_contract():
     assert q.observer.backend is Backend.VIRTUAL
     q.dims = 4
     assert q._broadcast_qparams(torch.ones(6)).shape == (6, 1, 1, 1)
+
+
+# ---------------------------------------------------------------- CalibrationRunner host logic (no kernels)
+class _StubCache(list):
+    def reset(self):
+        self.clear()
+
+
+class _StubObserver:
+    def __init__(self):
+        self.data_cache = _StubCache()
+
+
+class _StubQuantizer:
+    TYPE = "uniform"
+
+    def __init__(self, fused=False):
+        self.fake_fused = fused
+        self.seen, self.calcs = [], 0
+        self.observer = _StubObserver()
+
+    def update_observer(self, x):
+        self.seen.append(tuple(x.shape))
+
+    def calc_qparams(self):
+        self.calcs += 1
+
+
+def _stub_net():
+    import torch
+
+    class Opr(torch.nn.Module):
+        def __init__(self, has_weight, fused=False):
+            super().__init__()
+            self.input_quantizer = _StubQuantizer(fused)
+            self.weight_quantizer = _StubQuantizer() if has_weight else None
+            self.weight = torch.nn.Parameter(torch.ones(2, 2)) if has_weight else None
+            self.flags = None
+
+        def set_quant(self, w_quant=False, a_quant=False):
+            self.flags = (w_quant, a_quant)
+
+        def forward(self, x):
+            return x * 2 if self.weight is not None else x + 1
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = Opr(True), Opr(False, fused=True), Opr(True)
+
+        def forward(self, x):
+            h = self.a(x)
+            return self.c(self.b(h) + h)
+
+    return Net()
+
+
+def test_calibration_runner_streaming_and_replay_feed_the_same_batches():
+    import torch
+
+    from sparsebit_b200.quantization.tools import CalibrationRunner, trace_quant_model
+
+    batches = [torch.zeros(3, 4), torch.zeros(5, 4)]
+    for streaming, asym in ((True, False), (False, False), (True, True)):
+        net = trace_quant_model(_stub_net())
+        assert [n.op for n in net.graph.nodes].count("call_module") == 3  # quant operators stay leaves
+        runner = CalibrationRunner(net, streaming=streaming)
+        runner.prepare_calibration()
+        for x in batches:
+            net(x)
+        runner.layerwise_calibration(None, asym=asym, w_quant=asym, a_quant=asym)
+        assert all(len(m._forward_pre_hooks) == 0 for m in net.modules())
+        # live input quantizers see every batch once per pass (a replay after streaming feeds them again,
+        # after resetting the observers' caches)
+        expect = [(3, 4), (5, 4)] * (2 if (streaming and asym) else 1)
+        assert net.a.input_quantizer.seen == expect and net.c.input_quantizer.seen == expect
+        assert net.b.input_quantizer.seen == [] and net.b.input_quantizer.calcs == 0  # fake-fused: untouched
+        assert net.a.input_quantizer.calcs == 1 and net.c.weight_quantizer.calcs == 1
+        assert net.a.weight_quantizer.seen == [(2, 2)]
+        if asym or not streaming:
+            assert net.a.flags == (False, False)  # quant switched back off after each replayed node

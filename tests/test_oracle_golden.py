@@ -152,3 +152,19 @@ def test_c_restatement_matches_reference(golden):
     lib.sbo_gptq4(x.ctypes.data_as(vp), qw.ctypes.data_as(vp), out.ctypes.data_as(vp), sc.ctypes.data_as(vp),
                   zr.ctypes.data_as(vp), ctypes.c_int64(x.shape[0]), ctypes.c_int64(k), ctypes.c_int64(n), 128)
     np.testing.assert_allclose(out, gg[name + "_gt"], rtol=1e-5, atol=1e-5)
+
+
+def test_adaround_restatement_matches_reference(golden):
+    """oracle/qdq.py adaround_* vs the unmodified reference quantizer (adaround.py) incl. autograd's dL/dv."""
+    g = golden("next_rows")
+    for name in g["ada_cases"]:
+        qmin, qmax, ch_axis, perch, _, _ = (int(v) for v in g[name + "_meta"])
+        w, v0, v1, s, zp = (g[name + k] for k in ("_w", "_v0", "_v1", "_scale", "_zp"))
+        # hard rounding is integer work: bit-exact
+        assert _eq_bits(oqdq.adaround_forward(w, v1, s, zp, qmin, qmax, ch_axis, soft=False), g[name + "_yhard"]), name
+        # exp / log differ by an ulp between libms: float tolerance of the north star (1e-5 relative)
+        np.testing.assert_allclose(oqdq.adaround_init(w, s, ch_axis), v0, rtol=1e-5, atol=1e-6, err_msg=name)
+        np.testing.assert_allclose(oqdq.adaround_forward(w, v1, s, zp, qmin, qmax, ch_axis, soft=True), g[name + "_ysoft"],
+                                   rtol=1e-5, atol=1e-7, err_msg=name)
+        np.testing.assert_allclose(oqdq.adaround_grad_v(w, v1, s, zp, g[name + "_gy"], qmin, qmax, ch_axis), g[name + "_gv"],
+                                   rtol=1e-5, atol=1e-8, err_msg=name)
