@@ -242,6 +242,15 @@ size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_si
 int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales,
                        const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                        int group_size, void* workspace, size_t workspace_bytes, void* stream);
+/* Any bit width of the reference's module: bits = 4 forwards to sb200_gptq4_matmul; bits = 3 / 2
+ * replace vecquant3matmul / vecgroupquant3matmul / vecquant2matmul / vecgroupquant2matmul
+ * (cuda_kernel.cpp:26-57,68-72; cuda_kernel_3bit.cu, cuda_kernel_2bit.cu).  Packed layouts of
+ * QuantLinear.pack (utils/quant.py:210-258): 2-bit 16 values / word; 3-bit 32 values / 3 words with
+ * values 10 and 21 straddling; qweight rows = ceil(K*bits / (32*p)) * p (p = 3 for 3-bit, else 1).
+ * group_size: 0 = K, else a multiple of 64 (2-bit) / 128 (3-bit).  workspace is only used by bits = 4. */
+int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const float* scales,
+                      const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
+                      int bits, int group_size, void* workspace, size_t workspace_bytes, void* stream);
 /* Force a GPTQ implementation: 0 = auto, 1 = SIMT, 2 = tcgen05.  For tests / benchmarking. */
 int sb200_gptq4_set_impl(int impl);
 

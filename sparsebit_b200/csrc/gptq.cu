@@ -15,6 +15,8 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
              long long K, long long N, long long KW, int group_size, void* workspace, size_t workspace_bytes,
              cudaStream_t st);
 void gptq4_tc_set_trace(long long* p);
+int gptq_lowbit(int bits, const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+                long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
 static int g_gptq_impl = 0;
 }  // namespace sb200
 
@@ -75,6 +77,31 @@ int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const
   if (use_tc)
     return gptq4_tc(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, workspace, workspace_bytes, st);
   return gptq4_simt(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
+}
+
+int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+                      int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int bits, int group_size, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(bits == 2 || bits == 3 || bits == 4, "sb200_gptq_matmul: only support 2/3/4 bit now (got %d)", bits);
+  if (bits == 4)
+    return sb200_gptq4_matmul(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, workspace,
+                              workspace_bytes, stream);
+  SB_REQUIRE(x && qweight && out && scales && zeros, "sb200_gptq_matmul: null pointer argument");
+  SB_REQUIRE(m > 0 && k > 0 && n > 0, "sb200_gptq_matmul: empty operand (M=%lld K=%lld N=%lld)", (long long)m,
+             (long long)k, (long long)n);
+  SB_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && n < (1LL << 31), "sb200_gptq_matmul: dimension too large");
+  // rows QuantLinear allocates (utils/quant.py:172-184): ceil(K*bit / (32*p)) * p, p = 3 for 3-bit
+  const int64_t need = bits == 2 ? (k + 15) / 16 : ((k * 3 + 95) / 96) * 3;
+  SB_REQUIRE(qweight_rows >= need, "sb200_gptq_matmul: qweight has %lld rows, %d-bit K=%lld needs %lld",
+             (long long)qweight_rows, bits, (long long)k, (long long)need);
+  const int min_group = bits == 2 ? 64 : 128;  // cuda_kernel_2bit.cu:58, cuda_kernel_3bit.cu:60
+  if (group_size != 0) {
+    SB_REQUIRE(group_size > 0 && group_size % min_group == 0,
+               "only group_size divisible by %d is supported in %d-bit quantization (got %d)", min_group, bits, group_size);
+  } else {
+    group_size = (int)k;
+  }
+  return gptq_lowbit(bits, x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, (cudaStream_t)stream);
 }
 
 }  // extern "C"

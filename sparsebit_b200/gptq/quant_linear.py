@@ -1,16 +1,17 @@
-"""``QuantLinear`` for 4-bit GPTQ checkpoints (large_language_models/llama/quantization/utils/
-quant.py:147-307): same buffers (``qweight`` int32 [K/8, N], ``scales`` / ``zeros`` [N, G, 1] with
-zeros = zero * scale, ``bias``), same packed layout, same forward contract -- the matmul runs in
-``sb200_gptq4_matmul`` (tcgen05 tensor cores for prefill-sized M, HBM-bound SIMT for decode)."""
+"""``QuantLinear`` for 2 / 3 / 4-bit GPTQ checkpoints (large_language_models/llama/quantization/utils/
+quant.py:147-420): same buffers (``qweight`` int32 [rows, N], ``scales`` / ``zeros`` [N, G, 1] with
+zeros = zero * scale, ``bias``), same packed layouts, same forward contract -- the 4-bit matmul runs in
+``sb200_gptq4_matmul`` (tcgen05 tensor cores for prefill-sized M, HBM-bound SIMT for decode), 3 / 2-bit in
+``sb200_gptq_matmul`` (SIMT)."""
 import torch
 import torch.nn as nn
 
 from . import cuda_kernel
 
 
-def find_params_int4(weight, groupsize=-1):
-    """Asymmetric per-(row, group) 4-bit grid: GPTQ ``Quantizer.configure(bit=4, perchannel=True,
-    sym=False, mse=False)`` + ``find_params(weight=True)`` (utils/quant.py:43-89,117-124).
+def find_params(weight, bit=4, groupsize=-1):
+    """Asymmetric per-(row, group) grid: GPTQ ``Quantizer.configure(bit, perchannel=True, sym=False,
+    mse=False)`` + ``find_params(weight=True)`` (utils/quant.py:43-89,117-124).
     Returns (scale, zero) shaped [N, G, 1] (or [N, 1] when groupsize == -1)."""
     n, k = weight.shape
     groups = 1 if groupsize == -1 else k // groupsize
@@ -20,27 +21,85 @@ def find_params_int4(weight, groupsize=-1):
     dead = (lo == 0) & (hi == 0)
     lo = torch.where(dead, torch.full_like(lo, -1), lo)
     hi = torch.where(dead, torch.full_like(hi, 1), hi)
-    scale = (hi - lo) / 15
+    scale = (hi - lo) / (2**bit - 1)
     zero = torch.round(-lo / scale)
     shape = (n, groups, 1) if groups > 1 else (n, 1)
     return scale.reshape(shape), zero.reshape(shape)
 
 
-class Quant4Matmul(torch.autograd.Function):
-    """utils/quant.py:281-307: y = bias broadcast, then the kernel accumulates x @ W^T in place."""
+def _bit_positions(bit, k_padded):
+    """(word row, shift) of the LSB of every input channel, plus the straddle spill, for
+    QuantLinear.pack (utils/quant.py:210-258).  2/4-bit: 32/bit values per word.  3-bit: 32 values per
+    3 words, value 10 at bits 30-31 of word 0 + bit 0 of word 1, value 21 at bit 31 of word 1 + bits
+    0-1 of word 2."""
+    k = torch.arange(k_padded, dtype=torch.int64)
+    if bit in (2, 4):
+        per = 32 // bit
+        return k // per, (k % per) * bit
+    unit, j = k // 32, k % 32
+    word = torch.where(j <= 10, 0, torch.where(j <= 21, 1, 2))
+    shift = torch.where(j <= 10, 3 * j, torch.where(j <= 21, 3 * (j - 11) + 1, 3 * (j - 22) + 2))
+    return unit * 3 + word, shift
+
+
+def pack_rows(infeatures, bit):
+    """Rows of ``qweight``: ceil(K*bit / (32*p)) * p with p = 3 for 3-bit (utils/quant.py:172-184)."""
+    p = 3 if bit == 3 else 1
+    return -(-infeatures * bit // (32 * p)) * p
+
+
+def pack_intweight(q, bit):
+    """q: int64 [K, N] values in [0, 2^bit) -> int32 [rows, N] in the reference's packed layout."""
+    k, n = q.shape
+    rows = pack_rows(k, bit)
+    per_unit = {2: 16, 3: 32, 4: 8}[bit]
+    k_padded = -(-k // per_unit) * per_unit
+    padded = torch.zeros(k_padded, n, dtype=torch.int64)
+    padded[:k] = q
+    row, shift = _bit_positions(bit, k_padded)
+    words = torch.zeros(rows + 1, n, dtype=torch.int64)  # +1: spill row of a straddler in the last unit
+    shifted = padded << shift.view(-1, 1)
+    words.index_add_(0, row, shifted & 0xFFFFFFFF)
+    words.index_add_(0, row + 1, shifted >> 32)  # the straddling high bits (3-bit only; 0 otherwise)
+    words = words[:rows] & 0xFFFFFFFF
+    words = torch.where(words >= 2**31, words - 2**32, words)
+    return words.to(torch.int32)
+
+
+def find_params_int4(weight, groupsize=-1):
+    return find_params(weight, 4, groupsize)
+
+
+class QuantMatmul(torch.autograd.Function):
+    """Quant{2,3,4}Matmul (utils/quant.py:281-420): y = bias broadcast, then the kernel accumulates
+    x @ W^T in place."""
 
     @staticmethod
-    def forward(ctx, input, qweight, scales, zeros, bias, groupsize=-1):
+    def forward(ctx, input, qweight, scales, zeros, bias, groupsize=-1, bit=4):
         lead = list(input.shape[:-1])
         was_cuda = input.is_cuda
         dev = input.device if was_cuda else torch.device("cuda")
         x = input.to(dev).contiguous()
         y = bias.to(device=dev, dtype=x.dtype).expand(lead + [bias.numel()]).contiguous()
+        plain = {2: cuda_kernel.vecquant2matmul, 3: cuda_kernel.vecquant3matmul, 4: cuda_kernel.vecquant4matmul}[bit]
+        grouped = {2: cuda_kernel.vecgroupquant2matmul, 3: cuda_kernel.vecgroupquant3matmul,
+                   4: cuda_kernel.vecgroupquant4matmul}[bit]
+        args = (x, qweight.to(dev), y, scales.to(dev).contiguous(), zeros.to(dev).contiguous())
         if groupsize == -1:
-            cuda_kernel.vecquant4matmul(x, qweight.to(dev), y, scales.to(dev).contiguous(), zeros.to(dev).contiguous())
+            plain(*args)
         else:
-            cuda_kernel.vecgroupquant4matmul(x, qweight.to(dev), y, scales.to(dev).contiguous(), zeros.to(dev).contiguous(), groupsize)
+            grouped(*args, groupsize)
         return y if was_cuda else y.cpu()
+
+    @staticmethod
+    def backward(ctx, grad):
+        return (None,) * 7
+
+
+class Quant4Matmul(QuantMatmul):
+    @staticmethod
+    def forward(ctx, input, qweight, scales, zeros, bias, groupsize=-1):
+        return QuantMatmul.forward(ctx, input, qweight, scales, zeros, bias, groupsize, 4)
 
     @staticmethod
     def backward(ctx, grad):
@@ -50,11 +109,9 @@ class Quant4Matmul(torch.autograd.Function):
 class QuantLinear(nn.Module):
     def __init__(self, infeatures, outfeatures, bit=4, groupsize=-1):
         super().__init__()
-        if bit != 4:
-            raise NotImplementedError("sparsebit_b200 implements the int4 path named by the north star; "
-                                      "2/3-bit checkpoints are out of scope (SURVEY 8(f)#3)")
+        assert bit in [2, 3, 4], "only support 2/3/4 bit now"
         if groupsize != -1:
-            assert groupsize % 128 == 0
+            assert groupsize % {4: 128, 3: 128, 2: 64}[bit] == 0
             assert infeatures % groupsize == 0
         self.infeatures, self.outfeatures = infeatures, outfeatures
         self.bit, self.groupsize = bit, groupsize
@@ -63,12 +120,12 @@ class QuantLinear(nn.Module):
         self.register_buffer("zeros", torch.zeros(qshape))
         self.register_buffer("scales", torch.zeros(qshape))
         self.register_buffer("bias", torch.zeros(outfeatures))
-        self.register_buffer("qweight", torch.zeros(((infeatures + 7) // 8, outfeatures), dtype=torch.int32))
+        self.register_buffer("qweight", torch.zeros((pack_rows(infeatures, bit), outfeatures), dtype=torch.int32))
 
     @torch.no_grad()
     def pack(self, linear, scales, zeros):
-        """utils/quant.py:187-260 for bit = 4: nibble j of word (r, n) is the integer weight of
-        input channel 8 r + j, LSB first."""
+        """utils/quant.py:187-260: intweight = round((w + zero*scale) / scale), packed LSB first along K
+        (see ``_bit_positions``)."""
         self.zeros = (zeros * scales).to(self.zeros.dtype)
         self.scales = scales.clone()
         self.bias = linear.bias.clone() if linear.bias is not None else torch.zeros(self.outfeatures)
@@ -78,18 +135,12 @@ class QuantLinear(nn.Module):
             q = torch.round((w.view(self.outfeatures, self.groups, -1) + z) / s).view(self.outfeatures, self.infeatures)
         else:
             q = torch.round((w + z) / s)
-        q = q.to(torch.int64).t().contiguous()  # [K, N]
-        rows = (self.infeatures + 7) // 8
-        padded = torch.zeros(rows * 8, self.outfeatures, dtype=torch.int64)
-        padded[: self.infeatures] = q
-        shifts = (4 * torch.arange(8, dtype=torch.int64)).view(1, 8, 1)
-        words = (padded.view(rows, 8, self.outfeatures) << shifts).sum(dim=1) & 0xFFFFFFFF
-        words = torch.where(words >= 2**31, words - 2**32, words)
-        self.qweight = words.to(torch.int32)
+        self.qweight = pack_intweight(q.to(torch.int64).t().contiguous(), self.bit)
 
     def forward(self, x):
         # fp32 math like the reference (utils/quant.py:262-278), result cast back to x.dtype
-        y = Quant4Matmul.apply(x.float(), self.qweight, self.scales.float(), self.zeros.float(), self.bias.float(), self.groupsize)
+        y = QuantMatmul.apply(x.float(), self.qweight, self.scales.float(), self.zeros.float(), self.bias.float(),
+                              self.groupsize, self.bit)
         return y.to(x.dtype)
 
 

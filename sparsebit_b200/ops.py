@@ -343,3 +343,26 @@ def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0):
                                      m, k, n, qweight.shape[0], int(group_size), ws.data_ptr() if ws is not None else None,
                                      ws_bytes, _stream(x)))
     return out
+
+
+def gptq_matmul(x, qweight, out, scales, zeros, bits, group_size=0):
+    """In-place ``out += x @ dequant(qweight)`` for 2 / 3 / 4-bit GPTQ weights
+    (vecquant{2,3,4}matmul / vecgroupquant{2,3,4}matmul, cuda_kernel.cpp:10-57)."""
+    if int(bits) == 4:
+        return gptq4_matmul(x, qweight, out, scales, zeros, group_size)
+    lib = _lib.load()
+    _req(x, "inp1"), _req(out, "out"), _req(scales, "scales"), _req(zeros, "zeros")
+    _req(qweight, "inp2", torch.int32)
+    if x.dim() < 2:
+        raise SparsebitB200Error("input1 must be with dimension >= 2")  # cuda_kernel_3bit.cu:40
+    if qweight.dim() != 2:
+        raise SparsebitB200Error("input2 must be with dimension == 2")  # cuda_kernel_3bit.cu:44
+    k = x.shape[-1]
+    m = x.numel() // k
+    n = qweight.shape[1]
+    if out.shape[-1] != n:
+        raise SparsebitB200Error("output channel must be the same with input2 out_channel")  # :48
+    with torch.cuda.device(x.device):
+        check(lib.sb200_gptq_matmul(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(), zeros.data_ptr(),
+                                    m, k, n, qweight.shape[0], int(bits), int(group_size), None, 0, _stream(x)))
+    return out

@@ -226,6 +226,49 @@ def gen_gptq():
         out[name + "_gs"] = np.array(GS)
     out["cases"] = np.array(cases)
     save("gptq", **out)
+    # 3-bit / 2-bit rows: scaled-down mirrors of the bit=2,3 cases of test_cuda_kernel.py
+    out, cases = {}, []
+    for name, bit, bshape, M, N, GS in [
+        ("b3_single", 3, (1,), 1024, 40, -1),
+        ("b3_irregular", 3, (1,), 719, 157, -1),
+        ("b3_irregular_b31", 3, (31,), 333, 251, -1),
+        ("b3_tokens_4x8", 3, (4, 8), 256, 96, -1),
+        ("b3_group128_b29", 3, (29,), 512, 136, 128),
+        ("b3_group384_b4", 3, (4,), 768, 40, 384),
+        ("b2_single", 2, (1,), 1024, 40, -1),
+        ("b2_irregular", 2, (1,), 719, 157, -1),
+        ("b2_irregular_b31", 2, (31,), 333, 251, -1),
+        ("b2_tokens_4x8", 2, (4, 8), 256, 96, -1),
+        ("b2_group64_b29", 2, (29,), 512, 136, 64),
+        ("b2_group192_b4", 2, (4,), 768, 40, 192),
+    ]:
+        layer = torch.nn.Linear(M, N)
+        vec = torch.randn(bshape + (M,))
+        quantizer = Quantizer()
+        quantizer.configure(bit=bit, perchannel=True, sym=False, mse=False)
+        quantizer.find_params(layer.weight.data, weight=True, groupsize=GS)
+        layer.weight.data = quantize(
+            layer.weight.data.view(-1, M if GS == -1 else GS),
+            quantizer.scale.view(-1, 1),
+            quantizer.zero.view(-1, 1),
+            quantizer.maxq,
+        ).view(N, M)
+        ql = QuantLinear(M, N, bit=bit, groupsize=GS)
+        ql.pack(layer, quantizer.scale, quantizer.zero)
+        with torch.no_grad():
+            gt = layer(vec)
+        cases.append(name)
+        out[name + "_x"] = vec.numpy()
+        out[name + "_wdq"] = layer.weight.data.numpy()
+        out[name + "_qweight"] = ql.qweight.numpy()
+        out[name + "_scales"] = ql.scales.reshape(N, -1).numpy()
+        out[name + "_zeros"] = ql.zeros.reshape(N, -1).numpy()
+        out[name + "_zero_int"] = quantizer.zero.reshape(N, -1).numpy()
+        out[name + "_bias"] = ql.bias.detach().numpy()
+        out[name + "_gt"] = gt.numpy()
+        out[name + "_meta"] = np.array([bit, GS])
+    out["cases"] = np.array(cases)
+    save("gptq_lowbit", **out)
 
 
 def gen_next_rows():

@@ -201,3 +201,27 @@ def test_calibration_runner_streaming_and_replay_feed_the_same_batches():
         assert net.a.weight_quantizer.seen == [(2, 2)]
         if asym or not streaming:
             assert net.a.flags == (False, False)  # quant switched back off after each replayed node
+
+
+def test_quantlinear_pack_layouts_match_reference(golden):
+    """Host-side QuantLinear.pack (vectorised) vs the reference's packed words, all three bit widths."""
+    import torch
+
+    from sparsebit_b200.gptq.quant_linear import QuantLinear, pack_rows
+
+    for fixture in ("gptq", "gptq_lowbit"):
+        g = golden(fixture)
+        for name in g["cases"]:
+            bit, gs = (4, int(g[name + "_gs"])) if fixture == "gptq" else (int(v) for v in g[name + "_meta"])
+            wdq = torch.from_numpy(g[name + "_wdq"])
+            n, k = wdq.shape
+            lin = torch.nn.Linear(k, n)
+            lin.weight.data, lin.bias.data = wdq, torch.from_numpy(g[name + "_bias"])
+            s = torch.from_numpy(g[name + "_scales"])
+            zi = torch.from_numpy(g[name + "_zero_int"])
+            shape = (n, s.shape[1], 1) if gs != -1 else (n, 1)
+            ql = QuantLinear(k, n, bit=bit, groupsize=gs)
+            assert ql.qweight.shape == (pack_rows(k, bit), n)
+            ql.pack(lin, s.reshape(shape), zi.reshape(shape))
+            assert torch.equal(ql.qweight, torch.from_numpy(g[name + "_qweight"])), (name, bit)
+            assert torch.equal(ql.zeros.reshape(n, -1), torch.from_numpy(g[name + "_zeros"])), name

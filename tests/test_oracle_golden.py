@@ -168,3 +168,31 @@ def test_adaround_restatement_matches_reference(golden):
                                    rtol=1e-5, atol=1e-7, err_msg=name)
         np.testing.assert_allclose(oqdq.adaround_grad_v(w, v1, s, zp, g[name + "_gy"], qmin, qmax, ch_axis), g[name + "_gv"],
                                    rtol=1e-5, atol=1e-8, err_msg=name)
+
+
+def test_gptq_lowbit_matches_reference(golden):
+    """3-bit / 2-bit packing + matmul restatement vs the reference's QuantLinear.pack and its
+    Linear(dequantised W) ground truth (test_cuda_kernel.py bit=2,3 cases, scaled down)."""
+    g = golden("gptq_lowbit")
+    for name in g["cases"]:
+        bit, gs = (int(v) for v in g[name + "_meta"])
+        x, qw = g[name + "_x"], g[name + "_qweight"]
+        n, k = qw.shape[1], x.shape[-1]
+        s, z, zi = g[name + "_scales"], g[name + "_zeros"], g[name + "_zero_int"]
+        assert qw.shape[0] == ogptq.packed_rows(k, bit), name
+        q = ogptq.unpack_bits(qw, k, bit)
+        assert q.max() <= 2**bit - 1
+        gi = np.arange(k) // (k if gs == -1 else gs)
+        w = (s.T[gi] * q.astype(np.float32) - z.T[gi]).T
+        np.testing.assert_allclose(w, g[name + "_wdq"], rtol=0, atol=4e-7, err_msg=name)
+        # re-packing the dequantised weights gives the reference's words bit for bit
+        qw2, s2, z2 = ogptq.pack_bits(g[name + "_wdq"], s, zi, bit)
+        assert np.array_equal(qw2, qw), name
+        assert np.array_equal(z2, z), name
+        bias = np.broadcast_to(g[name + "_bias"], x.shape[:-1] + (n,))
+        y = ogptq.dequant_matmul(x, qw, bias, s, z, 0 if gs == -1 else gs, bit=bit)
+        np.testing.assert_allclose(y, g[name + "_gt"], rtol=1e-5, atol=1e-5, err_msg=name)
+        # parameter search restatement (scale is (max - min) / (2^bit - 1) of the float weights; the
+        # dequantised weights span the same range up to rounding at the ends)
+        s3, _ = ogptq.find_params(g[name + "_wdq"], bit, gs)
+        assert s3.shape == s.shape
