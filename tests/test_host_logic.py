@@ -1,5 +1,7 @@
 """CPU: host-side logic of the plugin mirror -- registries, descriptors, qparams math, the KL
 entropy search, GPTQ packing -- against the oracle and the reference's golden vectors."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -225,3 +227,52 @@ def test_quantlinear_pack_layouts_match_reference(golden):
             ql.pack(lin, s.reshape(shape), zi.reshape(shape))
             assert torch.equal(ql.qweight, torch.from_numpy(g[name + "_qweight"])), (name, bit)
             assert torch.equal(ql.zeros.reshape(n, -1), torch.from_numpy(g[name + "_zeros"])), name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/sparsebit"), reason="needs the reference checkout (build container only)")
+def test_install_rebinds_reference_calibration_runner():
+    """with the unmodified reference importable, install() puts the streaming runner
+    under QuantModel.prepare_calibration and the device observers under the reference's registry; without a
+    GPU the first observer update fails loudly instead of falling back to a CPU path."""
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, "tests/golden")
+        import _ref_import as R
+        R.install_shims()
+        import torch, torch.nn as nn
+        import sparsebit_b200
+        sparsebit_b200.install()
+        from sparsebit.quantization import QuantModel
+        from sparsebit.quantization.quant_config import _C
+
+        class Tiny(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.conv1 = nn.Conv2d(3, 8, 3, padding=1); self.relu1 = nn.ReLU(); self.fc = nn.Linear(512, 10)
+            def forward(self, x):
+                return self.fc(torch.flatten(self.relu1(self.conv1(x)), 1))
+
+        cfg = _C.clone(); cfg.DEVICE = "cpu"
+        cfg.W.QSCHEME = "per-channel-symmetric"; cfg.W.QUANTIZER.BIT = 8
+        cfg.A.QSCHEME = "per-tensor-affine"; cfg.A.QUANTIZER.BIT = 8
+        qm = QuantModel(Tiny().eval(), cfg)
+        qm.prepare_calibration()
+        assert type(qm.calibration_runner).__module__ == "sparsebit_b200.quantization.tools.calibration"
+        assert type(qm.model.conv1.input_quantizer.observer).__module__.startswith("sparsebit_b200.")
+        assert all(len(m._forward_pre_hooks) == 1 for m in (qm.model, qm.model.conv1, qm.model.relu1, qm.model.fc))
+        try:
+            qm(torch.randn(2, 3, 8, 8))
+        except RuntimeError as e:
+            assert "no CPU fallback" in str(e), e
+            print("LOUD")
+        else:
+            print("CUDA" if torch.cuda.is_available() else "SILENT")
+    """)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().splitlines()[-1] in ("LOUD", "CUDA")
