@@ -255,7 +255,7 @@ int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const 
 int sb200_gptq4_set_impl(int impl);
 
 /* Debug aid: when non-NULL, the tcgen05 kernel's CTA (0,0) writes clock64() stamps of its pipeline
- * handoffs into device_buffer[7][256] (event-major).  NULL disables tracing. */
+ * handoffs into device_buffer[13][256] (event-major).  NULL disables tracing. */
 int sb200_gptq4_set_trace(int64_t* device_buffer);
 
 /* Number of kernels this library launched since load (bench.py's `gpu_launches`). */

@@ -18,11 +18,19 @@
 //               SWIZZLE_128B) and for the PACKED weight tile (8 x 128 int32 = 4 KB)
 //   warps 12-19 unpack (two sets of 4 warps alternating stages, so one set's proxy fence / load
 //               latency overlaps the other's ALU work): packed words (shared) -> fp16 B tile in the
-//               canonical K-major SWIZZLE_128B UMMA layout (one int32 = 8 nibbles = one 16-byte chunk)
+//               canonical K-major SWIZZLE_128B UMMA layout (one int32 = 8 nibbles = one 16-byte chunk);
+//               one (x & mask) | bias LOP3 per nibble pair, the group's integer zero point prefetched as
+//               raw fp16 bits two stages ahead
 //   warp 1      MMA issuer: 4 x (hi, lo) tcgen05.mma.kind::f16 128x128x16 per stage, fp32 accumulators
-//               in TMEM, double buffered per K group; tcgen05.commit releases stages / publishes groups
-//   warps 4-11  epilogue: tcgen05.ld the group's 128x128 partial sums, fold in scale / zero / row sums
-//               into register accumulators, finally out += acc
+//               in TMEM, four buffers (all 512 columns) so the MMA runs up to 3 K groups ahead of the drain --
+//               the drain is the paced resource: 64 KB of tcgen05.ld per group at 64 B/clk = 1024 cycles
+//               against 512 cycles of tensor-core work; tcgen05.commit releases stages / publishes groups
+//   warps 4-11  epilogue: drain the group's 128x128 partial sums with software-pipelined tcgen05.ld.x16, fold
+//               in scale / zero / row sums into register accumulators, finally out += acc.  Every warp stages
+//               its own 64 scales one group ahead in a private double buffer (__syncwarp only, no CTA barrier)
+// Measured pacing (clock64 trace, scripts/gpu_tc_trace.py): per 128-K group the tensor core
+// needs 512 cycles, the drain chain of an epilogue warp ~2200 (tcgen05.ld.x16 round trips of ~350 cycles with 8
+// warps draining; TMEM read bandwidth is 64 B/clk = 1024 cycles per group at best), the unpack ~670 per stage.
 //   warp 2      TMEM allocator.
 // A prologue kernel splits x into (hi, lo), computes the per-(row, 128-K) sums and the row scales.
 #include <cuda.h>
@@ -39,8 +47,10 @@ constexpr int kTileN = 128;
 constexpr int kBlockK = 64;   // fp16 elements per stage = one 128-byte swizzle atom
 constexpr int kStages = 4;
 constexpr int kGroupK = 128;  // epilogue granularity (= the reference's BLOCKLEN)
-constexpr int kTcThreads = 640;  // 5 warpgroups: control | epilogue x2 | unpack x2
-constexpr uint32_t kTmemCols = 256;  // 2 accumulator buffers x 128 fp32 columns
+constexpr int kUnpackSets = 2;   // 4-warp unpack sets taking stages round-robin
+constexpr int kTcThreads = (12 + 4 * kUnpackSets) * 32;  // warpgroups: control | epilogue x2 | unpack x kUnpackSets
+constexpr int kAccBufs = 4;           // accumulator buffers in TMEM: the MMA runs up to 3 K groups ahead of the drain
+constexpr uint32_t kTmemCols = kAccBufs * kTileN;  // 4 x 128 fp32 columns = all of TMEM (1 CTA / SM)
 
 constexpr int kABytes = kTileM * kBlockK * 2;      // 16 KB  (hi or lo)
 constexpr int kBBytes = kTileN * kBlockK * 2;      // 16 KB  unpacked fp16 B tile
@@ -53,12 +63,13 @@ struct TcSmem {
   uint64_t full[kStages];
   uint64_t bready[kStages];
   uint64_t empty[kStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[kAccBufs];
+  uint64_t tmem_empty[kAccBufs];
   uint32_t tmem_base;
   uint32_t pad;
-  alignas(16) float sc[2][kTileN];
-  alignas(16) float zr[2][kTileN];
+  // per epilogue warp, double buffered: scales / zeros of the warp's 64 columns for one 128-K group
+  alignas(16) float scw[8][2][64];
+  alignas(16) float zrw[8][2][64];
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -100,6 +111,12 @@ __device__ __forceinline__ bool elect_one() {
       : "r"(0xFFFFFFFFu));
   return pred != 0;
 }
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "n"(MASK), "r"(c));
+  return r;
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -114,6 +131,24 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are threaded through the statement so that no use of them
+// can be scheduled above the wait
+__device__ __forceinline__ void tc_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // Register re-balancing between warpgroups (the kernel is launched with 65536 / 640 -> 96 registers per
 // thread; the epilogue needs ~130 for its 64 accumulators, the other roles far fewer).
@@ -241,7 +276,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       mbar_init(&sm->bready[s], 4);  // one arrive per warp of the unpack set that owns the stage
       mbar_init(&sm->empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAccBufs; ++b) {
       mbar_init(&sm->tmem_full[b], 1);
       mbar_init(&sm->tmem_empty[b], 8);  // one arrive per epilogue warp
     }
@@ -258,7 +293,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
 
-  if (warp < 4) reg_dec<56>();
+  if (warp < 4) reg_dec<40>();
   if (warp == 0) {
     // ================================================================== TMA producer
     if (lane == 0) {
@@ -286,9 +321,9 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        const int g = kb >> 1, b = g & 1;
+        const int g = kb >> 1, b = g & (kAccBufs - 1);
         if ((kb & 1) == 0) {  // first stage of a K group: the accumulator buffer must have been drained
-          mbar_wait(&sm->tmem_empty[b], (((uint32_t)(g >> 1)) & 1u) ^ 1u);
+          mbar_wait(&sm->tmem_empty[b], (((uint32_t)(g / kAccBufs)) & 1u) ^ 1u);
         }
         mbar_wait(&sm->bready[s], ph);
         tc_fence_after();
@@ -319,24 +354,28 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     }
   } else if (warp >= 12) {
     // ================================================================== unpack: packed int4 -> fp16 UMMA tile
-    reg_dec<56>();
+    if (kUnpackSets == 2) reg_dec<64>();  // room for all 8 output chunks: no STS source register is recycled early
     const int t = (threadIdx.x - 12 * 32) & 127;  // column of the tile
-    const int uset = (warp - 12) >> 2;             // this set handles stages kb with (kb & 1) == uset
+    const int uset = (warp - 12) >> 2;             // this set handles stages kb with kb % kUnpackSets == uset
+    uint32_t bias;
+    asm volatile("mov.b32 %0, 0x64006400;" : "=r"(bias));  // opaque to constant propagation
     // integer zero point of this column per K stage, fetched one iteration (two stages) ahead of its use;
     // the group index is advanced incrementally (no division in the loop)
     int gq_next = (uset * kBlockK) / group_size;
     int koff_next = uset * kBlockK;
-    auto zint_fetch = [&](int kb) -> float {
-      if (!int_zero || n0 + t >= N || kb >= num_kb) return 0.f;
-      return __half2float(__ldg(zint + (size_t)(n0 + t) * Gq + gq_next));
+    // (the raw fp16 bits are carried to the next iteration: converting at the fetch site would stall this
+    // warp on the global load right here -- 21 % of the unpack warps' samples in the ncu source view)
+    auto zint_fetch = [&](int kb) -> unsigned short {
+      if (!int_zero || n0 + t >= N || kb >= num_kb) return (unsigned short)0;
+      return __ldg(reinterpret_cast<const unsigned short*>(zint) + (size_t)(n0 + t) * Gq + gq_next);
     };
-    float z_cur = zint_fetch(uset);
-    for (int kb = uset; kb < num_kb; kb += 2) {
+    unsigned short z_cur = zint_fetch(uset);
+    for (int kb = uset; kb < num_kb; kb += kUnpackSets) {
       const int s = kb % kStages;
       const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-      koff_next += 2 * kBlockK;
+      koff_next += kUnpackSets * kBlockK;
       while (koff_next >= (gq_next + 1) * group_size) ++gq_next;
-      const float z_next = zint_fetch(kb + 2);
+      const unsigned short z_next = zint_fetch(kb + kUnpackSets);
       mbar_wait(&sm->full[s], ph);
       if (t == 0 && (warp & 3) == 0) SB_TRACE(1, kb);
       unsigned char* st = stage_base + (size_t)s * kStageBytes;
@@ -347,8 +386,9 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       uint32_t w[kBlockK / 8];
 #pragma unroll
       for (int r = 0; r < kBlockK / 8; ++r) w[r] = bq[r * kTileN + t];
+      if (tr && t == 0 && (warp & 3) == 0) { asm volatile("" ::"r"(w[0] ^ w[7])); SB_TRACE(7, kb); }
       // subtrahend: 1024 (the 0x6400 bias) plus, in integer-zero mode, the group's zero point
-      const float zsub = 1024.f + z_cur;
+      const float zsub = 1024.f + __half2float(__ushort_as_half(z_cur));
       z_cur = z_next;
       const __half2 sub = __float2half2_rn(zsub);
       const __half2 k16 = __float2half2_rn(0.0625f);
@@ -357,11 +397,13 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         // halves (n0,n4) (n1,n5) (n2,n6) (n3,n7).  0x6400 | q is the fp16 number 1024 + q; for the odd
         // nibbles the mask is applied in place (bits 4..7): 0x6400 | (q << 4) = 1024 + 16 q, brought back by
         // one exact HFMA2: (1024 + 16 q) / 16 - (64 + zero) ... folded as v * 1/16 + (64 - zsub) - 64 below.
+        // (x & mask) | bias as ONE LOP3 (immLut 0xEA): the bias sits in a register because a LOP3 takes a
+        // single immediate (with two the compiler emits an AND and an OR)
         const uint32_t lo = w[r], hi = w[r] >> 8;
-        const uint32_t v0 = (lo & 0x000F000Fu) | 0x64006400u;  // (n0, n4)
-        const uint32_t v1 = (lo & 0x00F000F0u) | 0x64006400u;  // 1024 + 16 * (n1, n5)
-        const uint32_t v2 = (hi & 0x000F000Fu) | 0x64006400u;  // (n2, n6)
-        const uint32_t v3 = (hi & 0x00F000F0u) | 0x64006400u;  // 1024 + 16 * (n3, n7)
+        const uint32_t v0 = and_or<0x000F000Fu>(lo, bias);  // (n0, n4)
+        const uint32_t v1 = and_or<0x00F000F0u>(lo, bias);  // 1024 + 16 * (n1, n5)
+        const uint32_t v2 = and_or<0x000F000Fu>(hi, bias);  // (n2, n6)
+        const uint32_t v3 = and_or<0x00F000F0u>(hi, bias);  // 1024 + 16 * (n3, n7)
         // (1024 + 16 q) * 1/16 = 64 + q exactly;  64 + q - (zsub - 960) = q - (zsub - 1024)
         const __half2 off = __hsub2(sub, __float2half2_rn(960.f));
         const __half2 h0 = __hsub2(*reinterpret_cast<const __half2*>(&v0), sub);
@@ -372,14 +414,18 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
                        *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
       }
+      if (t == 0 && (warp & 3) == 0) SB_TRACE(8, kb);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      if (t == 0 && (warp & 3) == 0) SB_TRACE(9, kb);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->bready[s]);
       if (t == 0 && (warp & 3) == 0) SB_TRACE(2, kb);
     }
   } else if (warp >= 4) {
     // ================================================================== epilogue (8 warps)
-    reg_inc<152>();  // (152-96)*256 <= (96-56)*384: must fit what the other warpgroups released
+    // two sets (640 threads, 96 regs at launch): (152-96)*256 <= (96-40)*128 + (96-64)*256
+    // one set  (512 threads, 128 at launch):     (152-128)*256 <= (128-24)*128
+    reg_inc<152>();
     const int e = threadIdx.x - 4 * 32;           // 0..255
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;              // which 64 columns
@@ -389,50 +435,59 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     float acc[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-    auto fetch = [&](int g, float& v_out, float& xs_out) {
-      // threads 0..127 fetch scale of column e, 128..255 the zero of column e - 128
-      const int c = e & (kTileN - 1);
-      const int n = n0 + c;
-      const int gq = (int)(((long long)g * kGroupK) / group_size);
-      const float* src = (e < kTileN) ? scales : zeros;
-      v_out = (n < N) ? __ldg(src + (size_t)n * Gq + gq) : 0.f;
+    // Every epilogue warp stages the scales (zeros) of its own 64 columns, one group ahead, in its private
+    // double buffer: the warps only __syncwarp, never meet at a CTA barrier, and so drift apart -- one warp's
+    // bookkeeping overlaps the other warps' TMEM drains (the drain is the paced resource; with a per-group
+    // bar.sync all 8 warps left the TMEM pipe idle together for ~900 of every ~2300 cycles).
+    float* my_sc = &sm->scw[warp - 4][0][0];
+    float* my_zr = &sm->zrw[warp - 4][0][0];
+    auto fetch = [&](int g, int gq, float (&v)[4], float& xs_out) {
+      const int na = n0 + col0 + lane, nb = na + 32;  // lane stages columns col0 + lane and col0 + 32 + lane
+      v[0] = (na < N) ? __ldg(scales + (size_t)na * Gq + gq) : 0.f;
+      v[1] = (nb < N) ? __ldg(scales + (size_t)nb * Gq + gq) : 0.f;
+      v[2] = (!int_zero && na < N) ? __ldg(zeros + (size_t)na * Gq + gq) : 0.f;
+      v[3] = (!int_zero && nb < N) ? __ldg(zeros + (size_t)nb * Gq + gq) : 0.f;
       xs_out = (m < M) ? __ldg(xsum + (size_t)m * G128 + g) : 0.f;
     };
-    float v_next, xs_next;
-    fetch(0, v_next, xs_next);
-    {
-      float* dst = (e < kTileN) ? sm->sc[0] : sm->zr[0];
-      dst[e & (kTileN - 1)] = v_next;
-    }
+    auto stage = [&](int b, const float (&v)[4]) {
+      my_sc[b * 64 + lane] = v[0];
+      my_sc[b * 64 + 32 + lane] = v[1];
+      if (!int_zero) {
+        my_zr[b * 64 + lane] = v[2];
+        my_zr[b * 64 + 32 + lane] = v[3];
+      }
+      __syncwarp();
+    };
+    float v_next[4], xs_next;
+    fetch(0, 0, v_next, xs_next);
+    stage(0, v_next);
     float xs = xs_next;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // quantisation group of the NEXT 128-K block, advanced incrementally (a 64-bit division here cost ~600
+    // cycles per group: the clock64 trace showed that gap between one group's drain and the next)
+    int gq_next = 0;
+    long long kend_next = group_size;  // first k that belongs to group gq_next + 1
     for (int g = 0; g < num_g; ++g) {
-      const int b = g & 1;
-      if (g + 1 < num_g) fetch(g + 1, v_next, xs_next);
-      mbar_wait(&sm->tmem_full[b], ((uint32_t)(g >> 1)) & 1u);
+      const int b = g & 1;                   // scale / zero staging buffer
+      const int tb = g & (kAccBufs - 1);     // accumulator buffer
+      if (g + 1 < num_g) {
+        const long long k_next = (long long)(g + 1) * kGroupK;
+        while (k_next >= kend_next) { ++gq_next; kend_next += group_size; }
+        fetch(g + 1, gq_next, v_next, xs_next);
+      }
+      mbar_wait(&sm->tmem_full[tb], ((uint32_t)(g / kAccBufs)) & 1u);
       if (e == 0) SB_TRACE(5, g);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * kTileN + col0);
-      const float4* sc4 = reinterpret_cast<const float4*>(&sm->sc[b][col0]);
-      const float4* zr4 = reinterpret_cast<const float4*>(&sm->zr[b][col0]);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tb * kTileN + col0);
+      const float4* sc4 = reinterpret_cast<const float4*>(my_sc + b * 64);
+      const float4* zr4 = reinterpret_cast<const float4*>(my_zr + b * 64);
       const float nxs = int_zero ? 0.f : -xs;  // integer-zero mode: the zero point is already inside the MMA
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        // 32 columns at a time (requesting both halves up front was measured slower: 100 ms vs 78 ms per
-        // LLaMA-7B prefill, the extra 32 live registers cost more than the second TMEM round trip)
-        uint32_t p[32];
-        tc_ld32(taddr + 32 * hh, p);
-        tc_wait_ld();
-        if (hh == 1) {  // both halves are in registers: buffer b may be overwritten by group g + 2
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->tmem_empty[b]);
-        }
+      // 16 columns of this thread's row: acc += scale * partial (- zero * xsum)
+      auto fold = [&](int c, const uint32_t (&p)[16]) {
         if (int_zero) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 s4 = sc4[8 * hh + j4];
-            const int o = 32 * hh + 4 * j4;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = sc4[4 * c + j4];
+            const int o = 16 * c + 4 * j4;
             acc[o + 0] = fmaf(s4.x, __uint_as_float(p[4 * j4 + 0]), acc[o + 0]);
             acc[o + 1] = fmaf(s4.y, __uint_as_float(p[4 * j4 + 1]), acc[o + 1]);
             acc[o + 2] = fmaf(s4.z, __uint_as_float(p[4 * j4 + 2]), acc[o + 2]);
@@ -440,22 +495,43 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
           }
         } else {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 s4 = sc4[8 * hh + j4], z4 = zr4[8 * hh + j4];
-            const int o = 32 * hh + 4 * j4;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 s4 = sc4[4 * c + j4], z4 = zr4[4 * c + j4];
+            const int o = 16 * c + 4 * j4;
             acc[o + 0] = fmaf(s4.x, __uint_as_float(p[4 * j4 + 0]), fmaf(z4.x, nxs, acc[o + 0]));
             acc[o + 1] = fmaf(s4.y, __uint_as_float(p[4 * j4 + 1]), fmaf(z4.y, nxs, acc[o + 1]));
             acc[o + 2] = fmaf(s4.z, __uint_as_float(p[4 * j4 + 2]), fmaf(z4.z, nxs, acc[o + 2]));
             acc[o + 3] = fmaf(s4.w, __uint_as_float(p[4 * j4 + 3]), fmaf(z4.w, nxs, acc[o + 3]));
           }
         }
-      }
+      };
+      // Software-pipelined drain: while 16 columns are folded, the next 16 are already on their way out of
+      // TMEM (the drain is the paced resource of this kernel: 64 KB per group at 64 B/clk).  tcgen05.wait::ld
+      // covers every outstanding load, so each load is issued right after the wait for the previous one.
+      uint32_t pa[16], pb[16];
+      tc_ld16(taddr, pa);
+      tc_wait_ld16(pa);
+      if (e == 0) SB_TRACE(10, g);
+      tc_ld16(taddr + 16, pb);
+      fold(0, pa);
+      tc_wait_ld16(pb);
+      tc_ld16(taddr + 32, pa);
+      fold(1, pb);
+      tc_wait_ld16(pa);
+      tc_ld16(taddr + 48, pb);
+      fold(2, pa);
+      tc_wait_ld16(pb);
+      if (e == 0) SB_TRACE(11, g);
+      // all 64 columns are in registers: the buffer may be overwritten by group g + kAccBufs
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->tmem_empty[tb]);
+      fold(3, pb);
+      if (e == 0) SB_TRACE(12, g);
       if (g + 1 < num_g) {
-        float* dst = (e < kTileN) ? sm->sc[b ^ 1] : sm->zr[b ^ 1];
-        dst[e & (kTileN - 1)] = v_next;
+        stage(b ^ 1, v_next);
         xs = xs_next;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (e == 0) SB_TRACE(6, g);
     }
     // out[m, n] += rowscale[m] * acc   (out is pre-initialised with the bias by the caller)
