@@ -44,7 +44,14 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-           "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+           "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_pipe_lsu.sum",
+           "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__inst_executed_pipe_alu.sum",
+           "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 
 
 def report(name):
@@ -64,8 +71,11 @@ def report(name):
     return "\n".join(out)
 
 
-open(f"profiles/{tag}_bench_launch_list.txt", "w").write(launch_list() + "\n")
-for name in ["prof_qdq_stats", "prof_gptq_tc", "prof_gptq_simt"]:
+try:
+    open(f"profiles/{tag}_bench_launch_list.txt", "w").write(launch_list() + "\n")
+except Exception as e:
+    print("launch list unchanged:", e)
+for name in ["prof_qdq_stats", "prof_gptq_tc", "prof_gptq_simt", "prof_gptq_lowbit"]:
     try:
         open(f"profiles/{tag}_{name}.txt", "w").write(report(name) + "\n")
     except Exception as e:
