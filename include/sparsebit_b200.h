@@ -188,6 +188,15 @@ int sb200_count_sign(const float* x, int64_t rows, int64_t row_len, int64_t* cou
 int sb200_percentile_ranks(const int64_t* counts, const int64_t* total, int64_t rows, double alpha,
                            uint64_t* sel, void* stream);
 
+/* Row moments for the step-size initialisations of LSQ (lsq.py:32-51: mean |x|), LSQ+ (lsq_plus.py:21-55:
+ * mean / unbiased std) and ACIQ-laplace (aciq.py:65-124: b = mean |x - mean x|).  x: [rows, row_len] contiguous.
+ *   out[row*5 + 0..4] += { sum x, sum x^2, sum |x|, sum |x - c|, sum (x - c)^2 },  c = centre[row] (0 if NULL)
+ * fp64 accumulation in a fixed order (deterministic); `out` is caller-zeroed and accumulates across batches.
+ * workspace: sb200_moments_workspace_bytes(rows, row_len) bytes of device memory. */
+size_t sb200_moments_workspace_bytes(int64_t rows, int64_t row_len);
+int sb200_observe_moments(const float* x, int64_t rows, int64_t row_len, const double* centre, double* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- (3) Sparser -------------------------------------------------------------------------
  * mask[i] = |w[i]| > thresh[0]   (sparse/sparsers/l1norm.py:23; strict, ties pruned; uint8 0/1 =
  * torch.bool storage).  thresh is a device float (from the radix select above with key_mode 1

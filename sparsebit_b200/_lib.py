@@ -54,6 +54,8 @@ PROTOTYPES = {
     "sb200_select_read": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "sb200_count_sign": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "sb200_percentile_ranks": (c_int, [c_vp, c_vp, c_i64, c_d, c_vp, c_vp]),
+    "sb200_moments_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "sb200_observe_moments": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sb200_mask_gt": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),

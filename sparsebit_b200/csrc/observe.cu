@@ -562,6 +562,70 @@ static inline int persistent_grid(long long tiles, int ctas_per_sm) {
   return (int)(tiles < cap ? tiles : cap);
 }
 
+
+// =========================================================================================
+// Row moments (LSQ / LSQ+ step-size initialisation, ACIQ-laplace): per row of x [rows, row_len]
+//   S[0] += sum x, S[1] += sum x^2, S[2] += sum |x|, S[3] += sum |x - c|, S[4] += sum (x - c)^2
+// (c = centre[row], 0 when centre is NULL).  fp32 loads, fp64 accumulation; one CTA per (row, tile)
+// writes its partial, a finish kernel adds the tiles of a row in index order -> deterministic.
+// =========================================================================================
+constexpr long long kMomTile = 16384;
+constexpr int kMomVals = 5;
+
+__global__ void __launch_bounds__(kThreads) moments_tile_kernel(const float* __restrict__ x, long long rows,
+                                                                long long row_len, const double* __restrict__ centre,
+                                                                double* __restrict__ partial) {
+  __shared__ double red[kMomVals][kThreads / 32];
+  const long long tpr = (row_len + kMomTile - 1) / kMomTile;
+  const long long total = rows * tpr;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const long long row = tile / tpr, j = tile - row * tpr;
+    const long long off = j * kMomTile;
+    const long long len = (row_len - off) < kMomTile ? (row_len - off) : kMomTile;
+    const float* p = x + row * row_len + off;
+    const float c = centre ? (float)centre[row] : 0.f;
+    const double cd = centre ? centre[row] : 0.0;
+    // per thread: fp32 partial sums over at most 64 elements would already lose bits for sum x^2; keep fp64
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    (void)c;
+    for (long long i = threadIdx.x; i < len; i += kThreads) {
+      const double v = (double)__ldcs(p + i);
+      const double d = v - cd;
+      a0 += v;
+      a1 += v * v;
+      a2 += fabs(v);
+      a3 += fabs(d);
+      a4 += d * d;
+    }
+    double acc[kMomVals] = {a0, a1, a2, a3, a4};
+#pragma unroll
+    for (int k = 0; k < kMomVals; ++k) {
+      const double w = warp_sum(acc[k]);
+      if (lane == 0) red[k][wid] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < kMomVals) {
+      double t = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t += red[threadIdx.x][w];
+      partial[tile * kMomVals + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void moments_finish_kernel(const double* __restrict__ partial, long long rows, long long tpr,
+                                      double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * kMomVals) return;
+  const long long row = i / kMomVals;
+  const int k = (int)(i - row * kMomVals);
+  double t = 0;
+  for (long long j = 0; j < tpr; ++j) t += partial[(row * tpr + j) * kMomVals + k];
+  out[i] += t;
+}
+
 }  // namespace sb200
 
 using namespace sb200;
@@ -725,6 +789,27 @@ int sb200_percentile_ranks(const int64_t* counts, const int64_t* total, int64_t 
   SB_REQUIRE(counts && total && sel && rows > 0, "sb200_percentile_ranks: bad arguments");
   percentile_ranks_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       (const unsigned long long*)counts, (const long long*)total, rows, alpha, (unsigned long long*)sel);
+  SB_LAUNCHED();
+  return SB200_OK;
+}
+
+size_t sb200_moments_workspace_bytes(int64_t rows, int64_t row_len) {
+  if (rows <= 0 || row_len <= 0) return 0;
+  return (size_t)(rows * ((row_len + kMomTile - 1) / kMomTile)) * kMomVals * sizeof(double);
+}
+
+int sb200_observe_moments(const float* x, int64_t rows, int64_t row_len, const double* centre, double* out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(x && out && workspace, "sb200_observe_moments: null pointer argument");
+  SB_REQUIRE(rows > 0 && row_len > 0, "sb200_observe_moments: empty tensor");
+  SB_REQUIRE(workspace_bytes >= sb200_moments_workspace_bytes(rows, row_len), "sb200_observe_moments: workspace too small");
+  const long long tpr = (row_len + kMomTile - 1) / kMomTile;
+  const long long tiles = rows * tpr;
+  double* partial = reinterpret_cast<double*>(workspace);
+  moments_tile_kernel<<<persistent_grid(tiles, 8), kThreads, 0, (cudaStream_t)stream>>>(x, rows, row_len, centre, partial);
+  SB_LAUNCHED();
+  const long long n = rows * kMomVals;
+  moments_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partial, rows, tpr, out);
   SB_LAUNCHED();
   return SB200_OK;
 }

@@ -107,6 +107,31 @@ def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, roundin
     return gx, gs, gzp
 
 
+# ----------------------------------------------------------------------------- row moments
+MOMENTS = 5  # sum x, sum x^2, sum |x|, sum |x - c|, sum (x - c)^2
+
+
+def moments_new(rows, device):
+    return torch.zeros(rows, MOMENTS, dtype=torch.float64, device=device)
+
+
+def moments_update(x2d, out, centre=None):
+    """Accumulate the fp64 row moments of x2d [rows, row_len] into ``out`` [rows, 5] (deterministic order)."""
+    lib = _lib.load()
+    _req(x2d, "data")
+    if x2d.dim() != 2 or out.shape != (x2d.shape[0], MOMENTS) or out.dtype != torch.float64:
+        raise SparsebitB200Error("moments_update: x2d must be [rows, row_len] and out float64 [rows, 5]")
+    if centre is not None and (centre.dtype != torch.float64 or centre.numel() != x2d.shape[0]):
+        raise SparsebitB200Error("moments_update: centre must hold one float64 per row")
+    rows, row_len = x2d.shape
+    ws_bytes = int(lib.sb200_moments_workspace_bytes(rows, row_len))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        check(lib.sb200_observe_moments(x2d.data_ptr(), rows, row_len, centre.data_ptr() if centre is not None else None,
+                                        out.data_ptr(), ws.data_ptr(), ws_bytes, _stream(x2d)))
+    return out
+
+
 # ----------------------------------------------------------------------------- AdaRound
 def _adaround_geometry(x, scale, ch_axis):
     if ch_axis is None:

@@ -4,12 +4,13 @@ Gaussian / Laplace shaped tensors.
 gaus: only min / max / element counts are needed -> the streaming MinMax kernels, nothing cached; the
 closing arithmetic on the handful of resulting scalars is done on the host with the reference's op order
 (torch-CUDA would turn ``tensor / python_float`` into a reciprocal multiply).  laplace: b = mean|x - mean(x)|
-is a two-pass float reduction over the cached batches (fp64 accumulation on the device; agrees with the
-reference to float rounding)."""
+is a two-pass reduction over the cached batches (``sb200_observe_moments``: fp64 accumulation in a fixed
+order; agrees with the reference to float rounding)."""
 import math
 
 import torch
 
+from ... import ops
 from ..common import QuantTarget
 from . import Observer as BaseObserver
 from . import register_observer
@@ -54,9 +55,14 @@ class Observer(BaseObserver):
         else:
             rows = self.data_cache.rows(self.is_perchannel)
             count = sum(r.shape[1] for r in rows)
-            mean = sum(r.sum(dim=1, dtype=torch.float64) for r in rows) / count
-            dev = sum((r.double() - mean.unsqueeze(1)).abs().sum(dim=1) for r in rows) / count
-            b = dev.to(torch.float32).cpu()
+            first = ops.moments_new(rows[0].shape[0], rows[0].device)
+            for r in rows:
+                ops.moments_update(r, first)
+            mean = (first[:, 0] / count).contiguous()
+            second = ops.moments_new(rows[0].shape[0], rows[0].device)
+            for r in rows:
+                ops.moments_update(r, second, centre=mean)
+            b = (second[:, 3] / count).to(torch.float32).cpu()
             if not self.is_perchannel:
                 b = b.reshape(())
             spread = (ALPHA_LAPLACE_POSITIVE if half else ALPHA_LAPLACE)[bit] * b

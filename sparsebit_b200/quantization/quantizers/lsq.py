@@ -11,6 +11,7 @@ import warnings
 import torch
 import torch.nn as nn
 
+from ... import ops
 from . import Quantizer as BaseQuantizer
 from . import register_quantizer
 from .quant_tensor import STE
@@ -57,17 +58,18 @@ class Quantizer(BaseQuantizer):
         if self.fake_fused or self.init_params:
             return self.scale, self.zero_point
         cache = self.observer.data_cache
-        rows = cache.rows(True)  # channel-first rows, like get_data_for_calibration(CHANNELWISE)
-        has_neg = any(bool((r < 0).any()) for r in rows)
-        if has_neg and not self.qdesc.is_symmetric:
+        # one native pass per cached batch: running min (negativity test) comes from the observer's streaming
+        # MinMax state, mean |x| from the fp64 row moments (sb200_observe_moments) -- no ATen reductions
+        running_min, _ = self.observer._running_minmax()
+        if bool((running_min < 0).any()) and not self.qdesc.is_symmetric:
             warnings.warn("Found data less than 0, reset quantizer scheme as symmetric")
             self.qdesc.set_symmetric(True)
-        if self.is_perchannel:
-            total = sum(r.abs().sum(dim=1, dtype=torch.float64) for r in rows)
-            count = sum(r.shape[1] for r in rows)
-        else:
-            total = sum(r.abs().sum(dtype=torch.float64) for r in rows)
-            count = sum(r.numel() for r in rows)
+        rows = cache.rows(self.is_perchannel)  # [C, M] per channel, [1, N] per tensor
+        acc = ops.moments_new(rows[0].shape[0], rows[0].device)
+        for r in rows:
+            ops.moments_update(r, acc)
+        count = sum(r.shape[1] for r in rows)
+        total = acc[:, 2] if self.is_perchannel else acc[0, 2]
         scale = (2 * (total / count) / math.sqrt(self.qdesc.qmax)).to(torch.float32)
         self.observer._reset()
         self.scale = nn.Parameter(self._broadcast_qparams(scale.to(self.device)))

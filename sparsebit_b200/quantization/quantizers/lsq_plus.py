@@ -4,6 +4,7 @@ mean +- 3 std step-size initialisation for per-channel-symmetric weights (lsq_pl
 import torch
 import torch.nn as nn
 
+from ... import ops
 from . import Quantizer as BaseQuantizer
 from . import register_quantizer
 from .lsq import GradScale, clamp_qparams, grad_scale_ratio
@@ -25,8 +26,19 @@ class Quantizer(BaseQuantizer):
         qd = self.qdesc
         if self.is_perchannel:
             assert self.is_symmetric, "LSQ+ only support per-channel-symmetric quant for weight"
-            rows = torch.cat(self.observer.data_cache.rows(True), dim=1)
-            std, mean = torch.std_mean(rows, dim=1)  # unbiased, like Tensor.std
+            # two native passes over the cached weights: mean, then the centred second moment (fp64, so the
+            # unbiased std agrees with Tensor.std to float rounding) -- sb200_observe_moments
+            rows = self.observer.data_cache.rows(True)
+            count = sum(r.shape[1] for r in rows)
+            first = ops.moments_new(rows[0].shape[0], rows[0].device)
+            for r in rows:
+                ops.moments_update(r, first)
+            mean64 = first[:, 0] / count
+            second = ops.moments_new(rows[0].shape[0], rows[0].device)
+            for r in rows:
+                ops.moments_update(r, second, centre=mean64.contiguous())
+            mean = mean64.to(torch.float32)
+            std = torch.sqrt(second[:, 4] / (count - 1)).to(torch.float32)
             scale = 2 * torch.maximum((mean - 3 * std).abs(), (mean + 3 * std).abs()) / (qd.qmax - qd.qmin)
             self.observer._reset()
             self.scale = nn.Parameter(self._broadcast_qparams(scale.to(self.device)))

@@ -182,3 +182,30 @@ def test_adaround_reconstruct_qlayer_reduces_error():
     with torch.no_grad():
         err_ada = (layer(x) - ref).pow(2).mean().item()
     assert err_ada <= err_nearest * 1.02, (err_ada, err_nearest)
+
+
+def test_row_moments_vs_fp64_numpy():
+    """sb200_observe_moments (LSQ / LSQ+ / ACIQ-laplace initialisation statistics): fp64 sums in a fixed order,
+    accumulated across batches, bit-identical run to run."""
+    from sparsebit_b200 import ops
+
+    rng = np.random.default_rng(11)
+    for rows, row_len in [(1, 100_003), (7, 33), (64, 20_000), (3, 1)]:
+        batches = [(rng.standard_normal((rows, row_len)) * 3 + 0.5).astype(np.float32) for _ in range(2)]
+        centre = rng.standard_normal(rows)
+        acc = ops.moments_new(rows, dev())
+        for b in batches:
+            ops.moments_update(t(b), acc, centre=torch.from_numpy(centre).to(dev()))
+        x = np.concatenate(batches, axis=1).astype(np.float64)
+        d = x - centre[:, None]
+        exp = np.stack([x.sum(1), (x * x).sum(1), np.abs(x).sum(1), np.abs(d).sum(1), (d * d).sum(1)], axis=1)
+        got = acc.cpu().numpy()
+        np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-9)
+        again = ops.moments_new(rows, dev())
+        for b in batches:
+            ops.moments_update(t(b), again, centre=torch.from_numpy(centre).to(dev()))
+        assert np.array_equal(again.cpu().numpy(), got)  # deterministic
+        plain = ops.moments_update(t(batches[0]), ops.moments_new(rows, dev())).cpu().numpy()
+        np.testing.assert_allclose(plain[:, 3], plain[:, 2], rtol=1e-15)  # centre = 0: |x - 0| == |x|
+    with pytest.raises(RuntimeError):
+        ops.moments_update(t(batches[0]), torch.zeros(2, 5, device=dev()))  # wrong dtype / shape
