@@ -1,5 +1,9 @@
-"""Sparser base (sparsebit/sparse/sparsers/base.py:6-25)."""
+"""Sparser plugin contract (the interface sparsebit/sparse/sparsers/base.py:6-25 exposes to SparseOpr):
+a module built from ``(config, opr)`` that turns a weight into a keep-mask via ``calc_mask``; the owning
+operator multiplies by that mask on every forward."""
 from torch import nn
+
+_KNOWN_TYPES = ("unstructed", "structed")  # spelling of the reference's config values
 
 
 class Sparser(nn.Module):
@@ -7,17 +11,26 @@ class Sparser(nn.Module):
 
     def __init__(self, config, opr):
         super().__init__()
-        self.config = config
-        self.opr = opr
-        self.type = config.SPARSER.TYPE
-        self.strategy = config.SPARSER.STRATEGY
-        self.ratio = config.SPARSER.RATIO
+        sparser_cfg = config.SPARSER
+        self.config, self.opr = config, opr
+        self.type, self.strategy = sparser_cfg.TYPE, sparser_cfg.STRATEGY
+        self.set_ratio(sparser_cfg.RATIO)
 
+    # -- plugin hook ---------------------------------------------------------------------------
     def calc_mask(self, x):
-        raise NotImplementedError
+        """Return a tensor shaped like ``x``: nonzero = keep.  Implemented by the registered strategies."""
+        raise NotImplementedError(f"{type(self).__name__} does not implement calc_mask")
 
+    # -- knobs the pruning schedules of the reference drive ---------------------------------------
     def set_ratio(self, ratio):
+        ratio = float(ratio)
+        if not 0.0 <= ratio <= 1.0:
+            raise ValueError(f"sparsity ratio must be in [0, 1], got {ratio}")
         self.ratio = ratio
 
+    @property
+    def is_structured(self):
+        return self.type == _KNOWN_TYPES[1]
+
     def __repr__(self):
-        return "{}, {}, {}".format(self.type, self.strategy, self.ratio)
+        return ", ".join(str(v) for v in (self.type, self.strategy, self.ratio))
