@@ -276,3 +276,30 @@ def test_install_rebinds_reference_calibration_runner():
     res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip().splitlines()[-1] in ("LOUD", "CUDA")
+
+
+def test_kl_entropy_screen_equals_index_exact_search():
+    """entropy_threshold's vectorised screen must return exactly what the index-exact restatement of
+    calibrate_entropy (kl_histogram.py:54-94) returns -- including histograms where some candidate's
+    divergence is ~0 and argmin does NOT land on the never-written slot."""
+    from sparsebit_b200.quantization.observers import kl_histogram as K
+
+    rng = np.random.default_rng(5)
+    hists = []
+    for trial in range(3):
+        x = rng.standard_normal(60_000) * (1 + trial)
+        x = np.abs(x) if trial == 1 else x
+        am = np.abs(x).max()
+        hists.append(np.histogram(x, bins=2048, range=(-am, am))[0].astype(np.float32))
+    x = np.round(rng.standard_normal(5000) * 2)  # sparse histogram: exercises the exact fallback
+    hists.append(np.histogram(x, bins=2048, range=(-np.abs(x).max(), np.abs(x).max()))[0].astype(np.float32))
+    hists += [np.zeros(2048, np.float32), np.eye(1, 2048, 1024, dtype=np.float32)[0] * 1000, np.ones(2048, np.float32)]
+    landed_elsewhere = 0
+    for h in hists:
+        for dst in (255, 15):
+            exact = K._entropy_threshold_exact(h, 1.0, 2048, dst)
+            assert K.entropy_threshold(h, 1.0, 2048, dst) == exact
+            landed_elsewhere += exact not in (769.0, 1009.0)
+    assert landed_elsewhere >= 3  # the fallback path was really taken
+    cand, div = K._divergences_fp64(hists[0], 2048, 255)
+    assert len(cand) == 897 and np.all(div > 1e-4)
