@@ -1,4 +1,13 @@
-"""Host-side mirror of the GPTQ int4 inference path of
-``large_language_models/llama/quantization``: the ``cuda_kernel`` module and ``QuantLinear``."""
+"""Host-side mirror of the GPTQ inference path of ``large_language_models/llama/quantization``: the
+``cuda_kernel`` module (4 / 3 / 2-bit entry points) and ``QuantLinear``."""
 from . import cuda_kernel  # noqa: F401
-from .quant_linear import Quant4Matmul, QuantLinear, find_params_int4, make_quant  # noqa: F401
+from .quant_linear import (  # noqa: F401
+    Quant4Matmul,
+    QuantLinear,
+    QuantMatmul,
+    find_params,
+    find_params_int4,
+    make_quant,
+    pack_intweight,
+    pack_rows,
+)
