@@ -263,6 +263,11 @@ int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const 
 /* Force a GPTQ implementation: 0 = auto, 1 = SIMT, 2 = tcgen05.  For tests / benchmarking. */
 int sb200_gptq4_set_impl(int impl);
 
+/* Tuning knob of the tcgen05 kernel: nanoseconds its mostly-waiting roles (TMA producer, MMA issuer waiting for a
+ * drained accumulator, unpack warps waiting for a stage) sleep between mbarrier polls.  0 (default) = poll
+ * continuously. */
+int sb200_gptq4_set_wait_backoff(int nanoseconds);
+
 /* Debug aid: when non-NULL, the tcgen05 kernel's CTA (0,0) writes clock64() stamps of its pipeline
  * handoffs into device_buffer[13][256] (event-major).  NULL disables tracing. */
 int sb200_gptq4_set_trace(int64_t* device_buffer);

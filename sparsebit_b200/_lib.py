@@ -68,6 +68,7 @@ PROTOTYPES = {
     "sb200_gptq_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_set_impl": (c_int, [c_int]),
     "sb200_gptq4_set_trace": (c_int, [c_vp]),
+    "sb200_gptq4_set_wait_backoff": (c_int, [c_int]),
 }
 
 SELECT_STATE_WORDS = 4

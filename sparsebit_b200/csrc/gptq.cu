@@ -15,6 +15,7 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
              long long K, long long N, long long KW, int group_size, void* workspace, size_t workspace_bytes,
              cudaStream_t st);
 void gptq4_tc_set_trace(long long* p);
+void gptq4_tc_set_backoff(int ns);
 int gptq_lowbit(int bits, const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                 long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
 static int g_gptq_impl = 0;
@@ -27,6 +28,12 @@ extern "C" {
 int sb200_gptq4_set_impl(int impl) {
   SB_REQUIRE(impl >= 0 && impl <= 2, "sb200_gptq4_set_impl: impl must be 0, 1 or 2 (got %d)", impl);
   g_gptq_impl = impl;
+  return SB200_OK;
+}
+
+int sb200_gptq4_set_wait_backoff(int nanoseconds) {
+  SB_REQUIRE(nanoseconds >= 0 && nanoseconds <= 100000, "sb200_gptq4_set_wait_backoff: 0..100000 ns (got %d)", nanoseconds);
+  gptq4_tc_set_backoff(nanoseconds);
   return SB200_OK;
 }
 

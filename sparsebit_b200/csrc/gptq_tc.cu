@@ -98,6 +98,23 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accum)
       : "memory");
 }
+// mbarrier wait with an optional back-off between polls: the producer / issuer / unpack roles spend most of their
+// time waiting, and every poll is an MIO operation competing with the LDS / STS / tcgen05.ld traffic of the
+// roles that are busy (sb200_gptq4_set_wait_backoff; 0 = poll continuously like mbar_wait).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int backoff_ns) {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (backoff_ns > 0) __nanosleep((unsigned)backoff_ns);
+  }
+}
 // elect.sync: exactly one lane of a converged warp gets `true`.  Unlike `lane == 0` the compiler knows the
 // guarded code runs on a single lane of a uniform warp and keeps tcgen05 operands in uniform registers
 // (no per-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY lane loop).
@@ -250,7 +267,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 const __grid_constant__ CUtensorMap map_q, float* __restrict__ out, const float* __restrict__ scales,
                 const float* __restrict__ zeros, const float* __restrict__ xsum, const float* __restrict__ rowscale,
                 const __half* __restrict__ zint, const int* __restrict__ int_zero_flag, int M, int K, int N, int Gq,
-                int G128, int group_size, long long* __restrict__ trace) {
+                int G128, int group_size, long long* __restrict__ trace, int backoff_ns) {
   extern __shared__ unsigned char smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), bookkeeping after them
   unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -300,7 +317,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-        mbar_wait(&sm->empty[s], ph ^ 1u);
+        mbar_wait_relaxed(&sm->empty[s], ph ^ 1u, backoff_ns);
         SB_TRACE(0, kb);
         unsigned char* st = stage_base + (size_t)s * kStageBytes;
         mbar_expect_tx(&sm->full[s], need_lo ? kTxBytes : kTxBytes - kABytes);
@@ -323,7 +340,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
         const int g = kb >> 1, b = g & (kAccBufs - 1);
         if ((kb & 1) == 0) {  // first stage of a K group: the accumulator buffer must have been drained
-          mbar_wait(&sm->tmem_empty[b], (((uint32_t)(g / kAccBufs)) & 1u) ^ 1u);
+          mbar_wait_relaxed(&sm->tmem_empty[b], (((uint32_t)(g / kAccBufs)) & 1u) ^ 1u, backoff_ns);
         }
         mbar_wait(&sm->bready[s], ph);
         tc_fence_after();
@@ -376,7 +393,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       koff_next += kUnpackSets * kBlockK;
       while (koff_next >= (gq_next + 1) * group_size) ++gq_next;
       const unsigned short z_next = zint_fetch(kb + kUnpackSets);
-      mbar_wait(&sm->full[s], ph);
+      mbar_wait_relaxed(&sm->full[s], ph, backoff_ns);
       if (t == 0 && (warp & 3) == 0) SB_TRACE(1, kb);
       unsigned char* st = stage_base + (size_t)s * kStageBytes;
       const uint32_t* bq = reinterpret_cast<const uint32_t*>(st + 2 * kABytes + kBBytes);
@@ -615,6 +632,8 @@ static TcWorkspace tc_layout(long long M, long long K, long long N = 0, long lon
 
 static long long* g_tc_trace = nullptr;
 void gptq4_tc_set_trace(long long* p) { g_tc_trace = p; }
+static int g_tc_backoff_ns = 0;
+void gptq4_tc_set_backoff(int ns) { g_tc_backoff_ns = ns; }
 
 bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
                         long long KW, int group_size) {
@@ -677,7 +696,8 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
   }
   const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)((N + kTileN - 1) / kTileN));
   gptq4_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_hi, map_lo, map_q, out, scales, zeros, xsum, rowscale, zint, flag,
-                                                  (int)M, (int)K, (int)N, Gq, G128, group_size, g_tc_trace);
+                                                  (int)M, (int)K, (int)N, Gq, G128, group_size, g_tc_trace,
+                                                  g_tc_backoff_ns);
   SB_LAUNCHED();
   return SB200_OK;
 }
