@@ -17,6 +17,8 @@ and the same resulting qparams, but:
 Under ``sparsebit_b200.distributed.enable(group)`` every rank streams its shard of the calibration set and
 the observers all-reduce their statistics inside ``calc_qparams`` -- the runner itself has no collective.
 """
+import functools
+
 import torch
 import torch.fx as fx
 
@@ -65,7 +67,7 @@ class CalibrationRunner:
         self.record_inputs = self.is_graph if record_inputs is None else record_inputs
         assert streaming or self.is_graph, "the layer-wise replay needs a torch.fx.GraphModule (trace_quant_model)"
         self._handles = []
-        self._inputs = []     # one tuple of positional inputs per calibration batch
+        self._inputs = {}     # placeholder name -> one entry per calibration batch
         self._order = []      # quant operators in first-execution order
         self._seen = set()
 
@@ -78,11 +80,35 @@ class CalibrationRunner:
                 seen.add(id(module))
                 self._handles.append(module.register_forward_pre_hook(self._feed_observer))
         if self.record_inputs:
-            self._handles.append(self.model.register_forward_pre_hook(self._record))
+            self._hook_graph_inputs()
         self.builder = self  # the reference asserts on this attribute (calibration.py:72)
 
-    def _record(self, module, args):
-        self._inputs.append(tuple(a.detach() if isinstance(a, torch.Tensor) else a for a in args))
+    def _hook_graph_inputs(self):
+        """Keep references to the calibration inputs for a possible replay.  Like the reference
+        (calibration.py:16-62) each graph input is captured at the first operator that consumes it -- its
+        QuantModel calls ``self.model.forward(...)`` directly (quant_model.py:206-207), which bypasses hooks
+        on the graph module itself; inputs consumed first by a function / method node fall back to a hook on
+        the graph module."""
+        placeholders = [n for n in self.model.graph.nodes if n.op == "placeholder"]
+        self._inputs = {p.name: [] for p in placeholders}
+        pending = set(placeholders)
+        for node in self.model.graph.nodes:
+            if node.op != "call_module":
+                continue
+            wanted = [(pos, a.name) for pos, a in enumerate(node.args) if isinstance(a, fx.Node) and a in pending]
+            if wanted:
+                module = self.model.get_submodule(node.target)
+                self._handles.append(module.register_forward_pre_hook(functools.partial(self._record_at_consumer, wanted=wanted)))
+                pending -= {a for a in node.args if isinstance(a, fx.Node)}
+        if pending:
+            order = [p.name for p in placeholders]
+            names = {p.name for p in pending}
+            self._handles.append(self.model.register_forward_pre_hook(
+                lambda module, args: [self._inputs[n].append(_detached(a)) for n, a in zip(order, args) if n in names] and None))
+
+    def _record_at_consumer(self, module, args, wanted):
+        for pos, name in wanted:
+            self._inputs[name].append(_detached(args[pos]))
 
     def _feed_observer(self, module, args):
         if id(module) not in self._seen:
@@ -108,13 +134,14 @@ class CalibrationRunner:
         if self.streaming and not wants_replay:
             self._finish_streaming()
         else:
-            assert self.is_graph and self._inputs, "AdaRound / asym calibration replays the graph: pass a GraphModule"
+            assert self.is_graph and self._inputs and all(self._inputs.values()), \
+                "AdaRound / asym calibration replays the graph: pass a GraphModule and run the calibration batches"
             if self.streaming:  # statistics gathered in pass 1 are recomputed per layer
                 for m in self._quant_oprs():
                     if _live(m.input_quantizer):
                         m.input_quantizer.observer.data_cache.reset()
             self._replay(asym, w_quant, a_quant)
-        self._inputs = []
+        self._inputs = {}
 
     def _quant_oprs(self):
         if self._order:
@@ -141,8 +168,7 @@ class CalibrationRunner:
         from ..quantizers.adaround import reconstruct_qlayer
 
         graph = self.model.graph
-        n_batches = len(self._inputs)
-        placeholders = [n for n in graph.nodes if n.op == "placeholder"]
+        n_batches = min(len(v) for v in self._inputs.values())
         float_env, quant_env = {}, {}
         pending = {n: len(n.users) for n in graph.nodes}
 
@@ -155,8 +181,7 @@ class CalibrationRunner:
 
         for node in graph.nodes:
             if node.op == "placeholder":
-                pos = placeholders.index(node)
-                float_env[node] = [batch[pos] for batch in self._inputs]
+                float_env[node] = self._inputs[node.name][:n_batches]
                 if asym:
                     quant_env[node] = float_env[node]
                 continue
@@ -211,6 +236,10 @@ class CalibrationRunner:
                 else:
                     raise NotImplementedError(node.op)
         return outs
+
+
+def _detached(x):
+    return x.detach() if isinstance(x, torch.Tensor) else x
 
 
 def _fetch_attr(root, target):
