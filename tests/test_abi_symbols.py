@@ -69,3 +69,29 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsparsebit_b200.so")
     with pytest.raises(_lib.SparsebitB200Error, match="no CPU"):
         _lib.load()
+
+
+def test_widened_entry_points_validate_before_launching():
+    """AdaRound, 3 / 2-bit GPTQ, row moments, tuning knobs: bad arguments are rejected on the host."""
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.sb200_adaround_fwd(p, p, p, p, p, 1, 1, 8, -8, 7, 2, None) == -1 and b"soft" in lib.sb200_last_error()
+    assert lib.sb200_adaround_fwd(p, p, p, p, p, 1, 1, 0, -8, 7, 0, None) == -1
+    assert lib.sb200_adaround_bwd(p, p, p, p, None, p, 1, 1, 8, -8, 7, None) == -1
+    assert lib.sb200_adaround_init(p, None, p, 1, 1, 8, None) == -1
+    # bits other than 2 / 3 / 4; group sizes (cuda_kernel_2bit.cu:58, cuda_kernel_3bit.cu:60); packed rows
+    assert lib.sb200_gptq_matmul(p, p, p, p, p, 1, 256, 8, 64, 5, 0, None, 0, None) == -1 and b"2/3/4" in lib.sb200_last_error()
+    assert lib.sb200_gptq_matmul(p, p, p, p, p, 1, 256, 8, 24, 3, 64, None, 0, None) == -1
+    assert b"divisible by 128" in lib.sb200_last_error()
+    assert lib.sb200_gptq_matmul(p, p, p, p, p, 1, 256, 8, 16, 2, 96, None, 0, None) == -1
+    assert b"divisible by 64" in lib.sb200_last_error()
+    assert lib.sb200_gptq_matmul(p, p, p, p, p, 1, 256, 8, 23, 3, 0, None, 0, None) == -1 and b"rows" in lib.sb200_last_error()
+    assert lib.sb200_gptq_matmul(p, p, p, p, p, 1, 256, 8, 15, 2, 0, None, 0, None) == -1
+    # row moments: workspace sizing is pure, too-small workspaces are refused
+    assert lib.sb200_moments_workspace_bytes(3, 16384) == 3 * 5 * 8
+    assert lib.sb200_moments_workspace_bytes(3, 16385) == 3 * 2 * 5 * 8
+    assert lib.sb200_moments_workspace_bytes(0, 5) == 0
+    assert lib.sb200_observe_moments(p, 3, 16385, None, p, p, 8, None) == -1 and b"workspace" in lib.sb200_last_error()
+    assert lib.sb200_gptq4_set_wait_backoff(-1) == -1
+    assert lib.sb200_gptq4_set_wait_backoff(0) == 0
