@@ -196,3 +196,38 @@ def test_gptq_lowbit_matches_reference(golden):
         # dequantised weights span the same range up to rounding at the ends)
         s3, _ = ogptq.find_params(g[name + "_wdq"], bit, gs)
         assert s3.shape == s.shape
+
+
+def test_c_restatement_widened_rows(golden):
+    """oracle/c: 3 / 2-bit GPTQ unpack + matmul and the AdaRound evaluation branch vs the reference's outputs."""
+    import ctypes
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "c", "libsb_oracle.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/c not built (run __graft_entry__.build())")
+    lib = ctypes.CDLL(path)
+    if not hasattr(lib, "sbo_gptq_bits"):
+        pytest.skip("oracle/c is stale (run __graft_entry__.build())")
+    vp, i64 = ctypes.c_void_p, ctypes.c_int64
+    g = golden("gptq_lowbit")
+    for name in ("b3_irregular", "b3_group128_b29", "b2_irregular", "b2_group64_b29", "b2_group192_b4"):
+        bit, gs = (int(v) for v in g[name + "_meta"])
+        x = np.ascontiguousarray(g[name + "_x"].reshape(-1, g[name + "_x"].shape[-1]))
+        qw = np.ascontiguousarray(g[name + "_qweight"])
+        n, k = qw.shape[1], x.shape[1]
+        out = np.ascontiguousarray(np.broadcast_to(g[name + "_bias"], (x.shape[0], n))).copy()
+        sc, zr = np.ascontiguousarray(g[name + "_scales"]), np.ascontiguousarray(g[name + "_zeros"])
+        lib.sbo_gptq_bits(x.ctypes.data_as(vp), qw.ctypes.data_as(vp), out.ctypes.data_as(vp), sc.ctypes.data_as(vp),
+                          zr.ctypes.data_as(vp), i64(x.shape[0]), i64(k), i64(n), 0 if gs == -1 else gs, bit)
+        np.testing.assert_allclose(out, g[name + "_gt"].reshape(-1, n), rtol=1e-5, atol=1e-5, err_msg=name)
+    g = golden("next_rows")
+    for name in g["ada_cases"]:
+        qmin, qmax, ch_axis, perch, _, _ = (int(v) for v in g[name + "_meta"])
+        w, v1 = np.ascontiguousarray(g[name + "_w"]), np.ascontiguousarray(g[name + "_v1"])
+        s, zp = np.ascontiguousarray(g[name + "_scale"]), np.ascontiguousarray(g[name + "_zp"])
+        outer, c, inner = (1, w.shape[0], w[0].size) if perch else (1, 1, w.size)
+        out = np.empty_like(w)
+        lib.sbo_adaround_hard(w.ctypes.data_as(vp), v1.ctypes.data_as(vp), s.ctypes.data_as(vp), zp.ctypes.data_as(vp),
+                              out.ctypes.data_as(vp), i64(outer), i64(c), i64(inner), qmin, qmax)
+        assert _eq_bits(out, g[name + "_yhard"]), name
