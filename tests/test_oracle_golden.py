@@ -231,3 +231,22 @@ def test_c_restatement_widened_rows(golden):
         lib.sbo_adaround_hard(w.ctypes.data_as(vp), v1.ctypes.data_as(vp), s.ctypes.data_as(vp), zp.ctypes.data_as(vp),
                               out.ctypes.data_as(vp), i64(outer), i64(c), i64(inner), qmin, qmax)
         assert _eq_bits(out, g[name + "_yhard"]), name
+
+
+def test_exact_division_schemes_on_cpu():
+    """oracle/c/validate_div.c: the kernels' two replacements for div.rn.f32 (fp64-reciprocal product; fp32
+    Markstein quotient + magic rounding with its acceptance guard) re-enacted with IEEE CPU arithmetic."""
+    import json
+    import os
+    import shutil
+    import subprocess
+
+    cdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "c")
+    if shutil.which("gcc") is None and shutil.which("cc") is None:
+        pytest.skip("no C compiler")
+    subprocess.run(["make", "-C", cdir, "validate_div"], check=True, capture_output=True)
+    res = subprocess.run([os.path.join(cdir, "validate_div"), "2000000", "7"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    out = json.loads(res.stdout)
+    assert out["exact_trick_mismatches"] == 0 and out["fast_path_mismatches"] == 0
+    assert out["cases"] > 5_000_000 and out["fast_path_accepted"] > 1_000_000
