@@ -486,6 +486,9 @@ def main():
                          "op chain of quant_tensor.py:181-184 + min/max (oracle/torch_port.py)"}
 
     # ---- secondary metric of BASELINE.json: GPTQ int4 g128 tok/s on the LLaMA-7B linear shapes ----------
+    # `reference_cuda_kernel` below is a BASELINE leg like `cpu_baseline`: the reference's own CUDA kernel (built
+    # from /root/reference into oracle/_ref/gptq_ref.so by oracle/build_ref.py) timed next to ours, because the
+    # north star states this target relative to it (>= 1.0x).  Nothing of ours runs through it.
     gptq = None
     if rank == 0 and world == 1 and not args.no_gptq:
         try:
