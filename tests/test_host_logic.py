@@ -306,3 +306,53 @@ def test_kl_entropy_screen_equals_index_exact_search():
     assert landed_elsewhere >= 3  # the fallback path was really taken
     cand, div = K._divergences_fp64(hists[0], 2048, 255)
     assert len(cand) == 897 and np.all(div > 1e-4)
+
+
+def test_tcgen05_numeric_scheme_meets_the_reference_tolerance():
+    """CPU emulation of the arithmetic the tcgen05 GPTQ kernel performs (gptq_tc.cu header): activations scaled
+    by a per-row power of two and split into fp16 hi + lo, exact int4 (minus integer zero) fp16 operands, fp32
+    accumulation per 128-K group, fp32 fold `acc += scale * partial`, final `out += rowscale * acc`.  The
+    scheme -- not a particular GPU -- must stay inside the reference's rtol = atol = 1e-5 (test_cuda_kernel.py:47)
+    against the fp64 oracle, including outlier activations and the fp16-exact single-pass mode."""
+    rng = np.random.default_rng(3)
+    k, n, gs = 1024, 48, 128
+    for case in ("normal", "outliers", "fp16_acts", "tiny_scales"):
+        w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+        if case == "tiny_scales":
+            w *= 1e-3
+        scale, zero = ogptq.find_params_int4(w, gs)
+        wq = ogptq.quantize_weight(w, scale, zero, gs)
+        qw, scales, zeros = ogptq.pack_int4(wq, scale, zero)
+        x = rng.standard_normal((9, k)).astype(np.float32)
+        if case == "outliers":
+            x[:, ::97] *= 300.0
+            x[3] *= 1e-4
+        if case == "fp16_acts":
+            x = x.astype(np.float16).astype(np.float32)
+        bias = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (9, n)), scales, zeros, gs)
+
+        q = ogptq.unpack_int4(qw, k).astype(np.float32)                      # [K, N], exact in fp16
+        zint = np.rint(zeros / scales).astype(np.float32)                     # integer zero points [N, G]
+        assert np.all(np.abs(zeros - zint * scales) <= np.abs(zeros) * 2.0**-20 + 1e-30)
+        amax = np.abs(x).max(axis=1)
+        e = np.where(amax > 0, np.floor(np.log2(np.maximum(amax, 1e-38))) - 14, 0).astype(np.int32)
+        xs = np.ldexp(x, -e[:, None]).astype(np.float32)                      # row max in [2^14, 2^15)
+        hi = xs.astype(np.float16)
+        lo = (xs - hi.astype(np.float32)).astype(np.float16)
+        if case == "fp16_acts":
+            assert not lo.any()                                               # the kernel skips the second MMA pass
+        acc = np.zeros((9, n), np.float32)
+        for g in range(k // gs):
+            sl = slice(g * gs, (g + 1) * gs)
+            b = (q[sl] - zint[:, g][None, :]).astype(np.float16)              # operand of the MMA, exact
+            assert np.array_equal(b.astype(np.float32), q[sl] - zint[:, g][None, :])
+            # fp16 x fp16 products are exact in fp32; the accumulation order of the tensor core is unspecified:
+            # emulate it with an fp32 running sum over k (the least favourable ordering a GPU could use)
+            part = np.zeros((9, n), np.float32)
+            for kk in range(gs):
+                part += hi[:, sl][:, kk:kk + 1].astype(np.float32) * b[kk][None, :].astype(np.float32)
+                part += lo[:, sl][:, kk:kk + 1].astype(np.float32) * b[kk][None, :].astype(np.float32)
+            acc = (acc + scales[:, g][None, :] * part).astype(np.float32)
+        got = (np.broadcast_to(bias, (9, n)) + np.ldexp(acc, e[:, None])).astype(np.float32)
+        np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-5, err_msg=case)
