@@ -103,7 +103,9 @@ int sb200_qdq_perchannel_fwd_host(const float* x_host, const float* scale_host,
  * quant_perchannel_backward (export.cc:7, fake_quant_tensor.cu:227-314).
  *   vq = round(x/s) + zp ;  gx = gy * [qmin <= vq <= qmax]
  *   gs  = sum gy * { round(x/s) - x/s  inside ; (qmin - zp) below ; (qmax - zp) above }
- *   gzp = sum -s * gy * [vq outside [qmin, qmax]]         (per-tensor semantics for both, Q4)
+ *   gzp = sum -s * gy * [vq outside [qmin, qmax]]         per-tensor (fake_quant_tensor.cu:126)
+ *   gzp = sum -s * gy * [vq outside [qmin, qmax)]         per-channel: the reference kernel counts vq == qmax
+ *                                                         as clipped (fake_quant_tensor.cu:264); reproduced as is
  * gs / gzp may be NULL (the reference's enable_gs / enable_gzp = requires_grad flags).  They are
  * produced by a deterministic two-stage reduction (fp32 per thread, fp64 across CTAs) instead of
  * float atomics.  `workspace` must hold sb200_qdq_bwd_workspace_bytes(...) bytes. */
@@ -116,6 +118,16 @@ int sb200_qdq_perchannel_bwd(const float* x, const float* scale, const float* ze
                              const float* grad_y, float* grad_x, float* grad_scale, float* grad_zp,
                              int64_t outer, int64_t channels, int64_t inner, int qmin, int qmax,
                              int rounding, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same as sb200_qdq_perchannel_bwd with `flags`: SB200_BWD_GZP_CLOSED selects the closed interval
+ * qmin <= vq <= qmax for the zero-point gradient, i.e. the rule of the reference's Python statement of the
+ * backward (MySTE.backward, quantizers/quant_tensor.py:62-69) and of its per-tensor kernel. */
+#define SB200_BWD_GZP_CLOSED 1
+int sb200_qdq_perchannel_bwd_ex(const float* x, const float* scale, const float* zero_point,
+                                const float* grad_y, float* grad_x, float* grad_scale, float* grad_zp,
+                                int64_t outer, int64_t channels, int64_t inner, int qmin, int qmax,
+                                int rounding, int flags, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* ---- (2) Observer calibration reductions -------------------------------------------------
  * MinMax (observers/minmax.py:14-25 -- torch.cat + min/max).  Streaming: the state is updated

@@ -61,15 +61,18 @@ def quantize_int(x, scale, zero_point, qmin, qmax, ch_axis=0, rounding=0):
         return _clamp_keep_nan((q + zp).astype(F32), qmin, qmax)
 
 
-def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0):
-    """STE backward.  The reference has no CPU implementation (quant_tensor.py:113-116); restated
+def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0, gzp_open_top=False):
+    """STE backward.  The production path has no CPU implementation (quant_tensor.py:113-116); restated
     from MySTE.backward (quant_tensor.py:46-71) and the CUDA kernels
     (torch_extensions/fake_quant_tensor.cu:111-131, 243-268), reductions in fp64:
         vq  = round(x/s) + zp
         gx  = gy * [qmin <= vq <= qmax]
         gs  = sum gy * (round(x/s) - x/s | qmin - zp | qmax - zp)
-        gzp = sum -s * gy * [vq outside]            (per-tensor rule for both layouts, Q4)
-    Returns gx (fp32), gs, gzp (fp64, shape [C] or [1])."""
+        gzp = sum -s * gy * [vq outside [qmin, qmax]]
+    ``gzp_open_top``: the reference's PER-CHANNEL kernel tests ``vq >= qmin && vq < qmax``
+    (fake_quant_tensor.cu:264), i.e. vq == qmax counts as clipped for the zero-point gradient only.
+    Pinned to MySTE.backward outputs (tests/golden/bwd.npz) and, on the GPU box, to the reference's own
+    kernels (tests/test_gpu_reference_ext.py).  Returns gx (fp32), gs, gzp (fp64, shape [C] or [1])."""
     x = np.asarray(x, dtype=F32)
     gy = np.asarray(grad_y, dtype=F32)
     s = _bcast(scale, x, ch_axis)
@@ -83,7 +86,8 @@ def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0
     gx = np.where(inside, gy, F32(0)).astype(F32)
     term = np.where(inside, (r - q).astype(F32), np.where(below, (F32(qmin) - zp).astype(F32), (F32(qmax) - zp).astype(F32)))
     gs_e = term.astype(np.float64) * gy.astype(np.float64)
-    gz_e = np.where(inside, 0.0, (-s).astype(np.float64) * gy.astype(np.float64))
+    inside_z = inside & (vq < F32(qmax)) if gzp_open_top else inside
+    gz_e = np.where(inside_z, 0.0, (-s).astype(np.float64) * gy.astype(np.float64))
     nch = np.asarray(scale).size
     if nch == 1:
         return gx, np.array([gs_e.sum()]), np.array([gz_e.sum()])

@@ -13,9 +13,11 @@
 // 12 B/elem (x, gy in; gx out).  The reference reduces gs/gzp with a block reduce + float
 // atomicAdd *per grid-stride iteration* and has __syncthreads() under divergent control flow
 // (fake_quant_tensor.cu:123,128,260,265); here every tile produces one fp64 partial that a second
-// tiny kernel sums in a fixed order -> deterministic, no atomics.  The per-channel gzp mask uses the
-// per-tensor rule (vq <= qmax is inside); the reference's per-channel kernel uses vq < qmax
-// (fake_quant_tensor.cu:264), which SURVEY.md Q4 identifies as a bug.
+// tiny kernel sums in a fixed order -> deterministic, no atomics.  Zero-point gradient rule: the reference's
+// per-tensor kernel and MySTE.backward treat qmin <= vq <= qmax as inside; its per-channel kernel uses
+// qmin <= vq < qmax (fake_quant_tensor.cu:264).  sb200_qdq_perchannel_bwd reproduces the
+// reference's per-channel kernel; sb200_qdq_perchannel_bwd_ex(flags = SB200_BWD_GZP_CLOSED) selects the
+// MySTE / per-tensor rule.
 #include "common.cuh"
 
 namespace sb200 {
@@ -39,7 +41,7 @@ __device__ __forceinline__ float bwd1(float x, float gy, const QP& p, float lo_t
   const bool inside = (vq >= p.qmin) && (vq <= p.qmax);
   const float term = inside ? __fsub_rn(r, q) : (below ? lo_term : hi_term);
   a.gs = fmaf(term, gy, a.gs);
-  a.gzp += inside ? 0.f : __fmul_rn(-p.s, gy);
+  a.gzp += ((vq >= p.qmin) && (vq <= p.gz_hi)) ? 0.f : __fmul_rn(-p.s, gy);
   return inside ? gy : 0.f;
 }
 
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) bwd_rows_kernel(const float* __restr
                                                             float* __restrict__ gx, const float* __restrict__ scale,
                                                             const float* __restrict__ zero_point, long long rows,
                                                             long long inner, int channels, float qmin, float qmax,
-                                                            int rounding, double2* __restrict__ partial) {
+                                                            float gz_hi, int rounding, double2* __restrict__ partial) {
   __shared__ double s_red[2][kThreads / 32];
   const long long tpr = (inner + kTile - 1) / kTile;
   const long long total = rows * tpr;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(kThreads) bwd_rows_kernel(const float* __restr
     p.set(__ldg(scale + c), __ldg(zero_point + c));
     p.qmin = qmin;
     p.qmax = qmax;
+    p.gz_hi = gz_hi;
     BwdAcc a = {0.f, 0.f};
     span_bwd<ROUNDING>(x + off, gy + off, gx + off, len, CTA_TILE ? threadIdx.x : lane, CTA_TILE ? blockDim.x : 32,
                        p, a, rounding);
@@ -191,8 +194,8 @@ template <int VEC, int ROUNDING>
 __global__ void __launch_bounds__(128) bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ gy,
                                                        float* __restrict__ gx, const float* __restrict__ scale,
                                                        const float* __restrict__ zero_point, long long R, int channels,
-                                                       long long rows_per_block, float qmin, float qmax, int rounding,
-                                                       double2* __restrict__ partial) {
+                                                       long long rows_per_block, float qmin, float qmax, float gz_hi,
+                                                       int rounding, double2* __restrict__ partial) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int nq = channels / VEC;
   if (q >= nq) return;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(128) bwd_cols_kernel(const float* __restrict__
     p[j].set(__ldg(scale + q * VEC + j), __ldg(zero_point + q * VEC + j));
     p[j].qmin = qmin;
     p[j].qmax = qmax;
+    p[j].gz_hi = gz_hi;
     lo_term[j] = __fsub_rn(qmin, p[j].zp);
     hi_term[j] = __fsub_rn(qmax, p[j].zp);
     a[j].gs = a[j].gzp = 0.f;
@@ -300,7 +304,9 @@ static size_t bwd_ws_bytes(long long outer, long long channels, long long inner)
 
 static int bwd_dispatch(const float* x, const float* scale, const float* zp, const float* gy, float* gx, float* gs,
                         float* gzp, long long outer, long long channels, long long inner, int qmin, int qmax,
-                        int rounding, void* workspace, size_t workspace_bytes, cudaStream_t st, const char* who) {
+                        int rounding, bool gzp_open_top, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                        const char* who) {
+  const float gz_hi = gzp_open_top ? (float)qmax - 1.f : (float)qmax;
   SB_REQUIRE(x && scale && zp && gy && gx, "%s: null pointer argument", who);
   SB_REQUIRE(outer > 0 && channels > 0 && inner > 0, "%s: Kernel Failure, Tensor is empty: data", who);
   SB_REQUIRE(qmin <= qmax, "%s: qmin > qmax", who);
@@ -322,7 +328,7 @@ static int bwd_dispatch(const float* x, const float* scale, const float* zp, con
     const long long nqv = vec ? channels / 4 : channels;
     const dim3 grid((unsigned)((nqv + 127) / 128), (unsigned)nb);
 #define SB_GOC(V_, R_) \
-  bwd_cols_kernel<V_, R_><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, rounding, partial)
+  bwd_cols_kernel<V_, R_><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, gz_hi, rounding, partial)
     if (vec) {
       if (rounding == 0) SB_GOC(4, 0); else SB_GOC(4, -1);
     } else {
@@ -342,7 +348,7 @@ static int bwd_dispatch(const float* x, const float* scale, const float* zp, con
   const bool cta_tile = inner >= 1024;
 #define SB_GO(CT_, R_)                                                                                   \
   bwd_rows_kernel<CT_, R_><<<persistent_grid(CT_ ? tiles : (tiles + 7) / 8, 8), kThreads, 0, st>>>(     \
-      x, gy, gx, scale, zp, rows, inner, (int)channels, (float)qmin, (float)qmax, rounding, partial)
+      x, gy, gx, scale, zp, rows, inner, (int)channels, (float)qmin, (float)qmax, gz_hi, rounding, partial)
   if (cta_tile) {
     if (rounding == 0) SB_GO(true, 0); else SB_GO(true, -1);
   } else {
@@ -370,7 +376,7 @@ size_t sb200_qdq_bwd_workspace_bytes(int64_t outer, int64_t channels, int64_t in
 int sb200_qdq_pertensor_bwd(const float* x, const float* scale, const float* zero_point, const float* grad_y,
                             float* grad_x, float* grad_scale, float* grad_zp, int64_t n, int qmin, int qmax,
                             int rounding, void* workspace, size_t workspace_bytes, void* stream) {
-  return bwd_dispatch(x, scale, zero_point, grad_y, grad_x, grad_scale, grad_zp, 1, 1, n, qmin, qmax, rounding,
+  return bwd_dispatch(x, scale, zero_point, grad_y, grad_x, grad_scale, grad_zp, 1, 1, n, qmin, qmax, rounding, false,
                       workspace, workspace_bytes, (cudaStream_t)stream, "sb200_qdq_pertensor_bwd");
 }
 
@@ -379,7 +385,17 @@ int sb200_qdq_perchannel_bwd(const float* x, const float* scale, const float* ze
                              int64_t inner, int qmin, int qmax, int rounding, void* workspace, size_t workspace_bytes,
                              void* stream) {
   return bwd_dispatch(x, scale, zero_point, grad_y, grad_x, grad_scale, grad_zp, outer, channels, inner, qmin, qmax,
-                      rounding, workspace, workspace_bytes, (cudaStream_t)stream, "sb200_qdq_perchannel_bwd");
+                      rounding, true, workspace, workspace_bytes, (cudaStream_t)stream, "sb200_qdq_perchannel_bwd");
+}
+
+int sb200_qdq_perchannel_bwd_ex(const float* x, const float* scale, const float* zero_point, const float* grad_y,
+                                float* grad_x, float* grad_scale, float* grad_zp, int64_t outer, int64_t channels,
+                                int64_t inner, int qmin, int qmax, int rounding, int flags, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  SB_REQUIRE((flags & ~SB200_BWD_GZP_CLOSED) == 0, "sb200_qdq_perchannel_bwd_ex: unknown flags 0x%x", flags);
+  return bwd_dispatch(x, scale, zero_point, grad_y, grad_x, grad_scale, grad_zp, outer, channels, inner, qmin, qmax,
+                      rounding, (flags & SB200_BWD_GZP_CLOSED) == 0, workspace, workspace_bytes, (cudaStream_t)stream,
+                      "sb200_qdq_perchannel_bwd_ex");
 }
 
 }  // extern "C"

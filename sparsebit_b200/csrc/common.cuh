@@ -107,6 +107,8 @@ struct QP {
   double rs;  // RN64(1 / s)
   float r;    // RN32(1 / s)
   bool fast;  // |s| in [2^-60, 2^60]: the fp32 fast path below is valid
+  float gz_hi;  // STE backward only: largest vq that counts as "inside" for the zero-point gradient (qmax, or qmax - 1
+                // under the reference's per-channel rule, fake_quant_tensor.cu:264)
   __device__ __forceinline__ void set(float scale, float zero_point_raw) {
     s = scale;
     zp = rintf(zero_point_raw);

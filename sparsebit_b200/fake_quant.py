@@ -29,8 +29,11 @@ def quant_pertensor_backward(data, scale, zero_point, grad_y, qmin, qmax, roundi
     return [gx, gs, gzp]
 
 
-def quant_perchannel_backward(data, scale, zero_point, grad_y, qmin, qmax, ch_axis, rounding):
-    """QuantizePerChannelBackward (fake_quant_tensor.cu:273-314)."""
+def quant_perchannel_backward(data, scale, zero_point, grad_y, qmin, qmax, ch_axis, rounding, gzp_closed=False):
+    """QuantizePerChannelBackward (fake_quant_tensor.cu:273-314).  The zero-point gradient follows the
+    reference kernel (vq == qmax counts as clipped, :264); ``gzp_closed=True`` (an extension, not part of
+    the reference signature) switches to MySTE.backward's closed interval (quant_tensor.py:62-69)."""
     gx, gs, gzp = ops.qdq_backward(data, scale, zero_point, grad_y, qmin, qmax, ch_axis, rounding,
-                                   need_gs=scale.requires_grad, need_gzp=zero_point.requires_grad)
+                                   need_gs=scale.requires_grad, need_gzp=zero_point.requires_grad,
+                                   gzp_closed=gzp_closed)
     return [gx, gs, gzp]

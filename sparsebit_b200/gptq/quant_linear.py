@@ -49,19 +49,30 @@ def pack_rows(infeatures, bit):
 
 
 def pack_intweight(q, bit):
-    """q: int64 [K, N] values in [0, 2^bit) -> int32 [rows, N] in the reference's packed layout."""
+    """q: int64 [K, N] values in [0, 2^bit) -> int32 [rows, N] in the reference's packed layout.  Runs on
+    q's device (the full-size reference test shapes, 12288 x 49152, are packed on the GPU)."""
     k, n = q.shape
     rows = pack_rows(k, bit)
     per_unit = {2: 16, 3: 32, 4: 8}[bit]
     k_padded = -(-k // per_unit) * per_unit
-    padded = torch.zeros(k_padded, n, dtype=torch.int64)
-    padded[:k] = q
-    row, shift = _bit_positions(bit, k_padded)
-    words = torch.zeros(rows + 1, n, dtype=torch.int64)  # +1: spill row of a straddler in the last unit
-    shifted = padded << shift.view(-1, 1)
-    words.index_add_(0, row, shifted & 0xFFFFFFFF)
-    words.index_add_(0, row + 1, shifted >> 32)  # the straddling high bits (3-bit only; 0 otherwise)
-    words = words[:rows] & 0xFFFFFFFF
+    if k_padded != k:
+        padded = torch.zeros(k_padded, n, dtype=torch.int64, device=q.device)
+        padded[:k] = q
+    else:
+        padded = q
+    if bit in (2, 4):  # no straddling values: word r = sum_j q[per*r + j] << (bit*j)
+        words = torch.zeros(rows, n, dtype=torch.int64, device=q.device)
+        v = padded.view(rows, per_unit, n)
+        for j in range(per_unit):
+            words |= v[:, j, :] << (bit * j)
+    else:
+        row, shift = _bit_positions(bit, k_padded)
+        row, shift = row.to(q.device), shift.to(q.device)
+        words = torch.zeros(rows + 1, n, dtype=torch.int64, device=q.device)  # +1: spill row of a straddler in the last unit
+        shifted = padded << shift.view(-1, 1)
+        words.index_add_(0, row, shifted & 0xFFFFFFFF)
+        words.index_add_(0, row + 1, shifted >> 32)  # the straddling high bits
+        words = words[:rows] & 0xFFFFFFFF
     words = torch.where(words >= 2**31, words - 2**32, words)
     return words.to(torch.int32)
 
@@ -129,8 +140,8 @@ class QuantLinear(nn.Module):
         self.zeros = (zeros * scales).to(self.zeros.dtype)
         self.scales = scales.clone()
         self.bias = linear.bias.clone() if linear.bias is not None else torch.zeros(self.outfeatures)
-        w = linear.weight.data.float().cpu()
-        z, s = self.zeros.float().cpu(), self.scales.float().cpu()
+        w = linear.weight.data.float()  # packs on the weight's device (CPU like the reference, or the GPU)
+        z, s = self.zeros.float().to(w.device), self.scales.float().to(w.device)
         if self.groups > 1:
             q = torch.round((w.view(self.outfeatures, self.groups, -1) + z) / s).view(self.outfeatures, self.infeatures)
         else:

@@ -76,9 +76,15 @@ def qdq_stats_pertensor(x, scale, zero_point, qmin, qmax, state, rounding=0, out
 
 
 # ----------------------------------------------------------------------------- STE backward
-def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, rounding=0, need_gs=True, need_gzp=True):
+BWD_GZP_CLOSED = 1  # include/sparsebit_b200.h SB200_BWD_GZP_CLOSED
+
+
+def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, rounding=0, need_gs=True, need_gzp=True,
+                 gzp_closed=False):
     """Returns (gx, gs, gzp); gs / gzp shaped like scale / zero_point (zeros when not requested,
-    like the reference which returns zeros_like, fake_quant_tensor.cu:147-149)."""
+    like the reference which returns zeros_like, fake_quant_tensor.cu:147-149).  Per-channel zero-point
+    gradient: by default the reference kernel's rule (vq == qmax counts as clipped, fake_quant_tensor.cu:264);
+    ``gzp_closed=True`` selects MySTE.backward's closed interval (quant_tensor.py:62-69)."""
     lib = _lib.load()
     _req(x, "data"), _req(scale, "scale"), _req(zero_point, "zero_point"), _req(grad_y, "grad")
     if grad_y.shape != x.shape:
@@ -90,6 +96,8 @@ def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, roundin
         outer, c, inner = 1, 1, x.numel()
     else:
         outer, c, inner = channel_geometry(x.shape, ch_axis)
+        if scale.numel() != c or zero_point.numel() != c:
+            raise SparsebitB200Error(f"per-channel qparams need {c} elements (got {scale.numel()}, {zero_point.numel()})")
     need = need_gs or need_gzp
     ws_bytes = int(lib.sb200_qdq_bwd_workspace_bytes(outer, c, inner)) if need else 0
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
@@ -100,10 +108,11 @@ def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, roundin
                                               gzp.data_ptr() if need_gzp else None, x.numel(), int(qmin), int(qmax),
                                               int(rounding), ws.data_ptr(), ws_bytes, _stream(x)))
         else:
-            check(lib.sb200_qdq_perchannel_bwd(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), grad_y.data_ptr(),
-                                               gx.data_ptr(), gs.data_ptr() if need_gs else None,
-                                               gzp.data_ptr() if need_gzp else None, outer, c, inner, int(qmin),
-                                               int(qmax), int(rounding), ws.data_ptr(), ws_bytes, _stream(x)))
+            check(lib.sb200_qdq_perchannel_bwd_ex(x.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), grad_y.data_ptr(),
+                                                  gx.data_ptr(), gs.data_ptr() if need_gs else None,
+                                                  gzp.data_ptr() if need_gzp else None, outer, c, inner, int(qmin),
+                                                  int(qmax), int(rounding), BWD_GZP_CLOSED if gzp_closed else 0,
+                                                  ws.data_ptr(), ws_bytes, _stream(x)))
     return gx, gs, gzp
 
 

@@ -8,6 +8,7 @@ and serve as known-answer inputs for the CUDA parity tests (tests/test_gpu_*.py)
 Reference entry points exercised (paths relative to /root/reference):
   sparsebit/quantization/quantizers/quant_tensor.py:159-185  ort_fake_quant (CPU branch :181-184)
   sparsebit/quantization/quantizers/quant_tensor.py:128-156  trt_fake_quant (CPU branch :154-155)
+  sparsebit/quantization/quantizers/quant_tensor.py:46-71    MySTE.backward (STE backward, Python statement)
   sparsebit/quantization/quantizers/base.py:33-39,66-68      Quantizer.update_observer / calc_qparams
   sparsebit/quantization/observers/{minmax,mse,percentile,kl_histogram}.py
   sparsebit/sparse/sparsers/l1norm.py:14-26                  unstructured mask
@@ -433,11 +434,69 @@ def gen_calibration():
     save("calibration", **out)
 
 
+def gen_bwd():
+    """STE backward known answers from the reference's own Python statement of it, ``MySTE.backward``
+    (sparsebit/quantization/quantizers/quant_tensor.py:46-71; the production ``STE.backward`` is CUDA-only,
+    :113-116).  ``MySTE.backward`` returns the ELEMENTWISE scale / zero-point gradient terms; they are stored
+    as such (fp32) and reduced by the consumer.  ``ctx`` is a stand-in carrying what ``MySTE.forward`` saves
+    (x, scale, zero_point.round(), qdesc)."""
+    from sparsebit.quantization.quantizers.quant_tensor import MySTE
+
+    g = torch.Generator().manual_seed(4242)
+    out, cases = {}, []
+    specs = [
+        # name, shape, qscheme, bit, target, layout, scale multiplier (< 1 forces clipping)
+        ("pt_sym8", (4, 3, 16, 16), "per-tensor-symmetric", 8, "feature", "NCHW", 0.5),
+        ("pt_aff8", (4, 3, 16, 16), "per-tensor-affine", 8, "feature", "NCHW", 0.7),
+        ("pt_aff4", (5, 37), "per-tensor-affine", 4, "feature", "NCHW", 1.0),
+        ("pc_w_sym8", (6, 4, 3, 3), "per-channel-symmetric", 8, "weight", None, 0.6),
+        ("pc_w_aff4", (7, 11), "per-channel-affine", 4, "weight", None, 0.8),
+        ("pc_a_nchw_sym4", (3, 5, 7, 7), "per-channel-symmetric", 4, "feature", "NCHW", 0.5),
+        ("pc_a_nlc_aff8", (3, 6, 8), "per-channel-affine", 8, "feature", "NLC", 0.7),
+    ]
+    for name, shape, scheme, bit, target, layout, mult in specs:
+        cfg = R.make_cfg(scheme, bit, target, "minmax", layout or "NCHW")
+        q = build_quantizer(cfg)
+        q.set_backend(Backend.VIRTUAL)
+        x = torch.randn(shape, generator=g) * 1.5
+        if "aff" in name and target == "feature":
+            x = torch.relu(x)
+        q.update_observer(x)
+        scale, zp = q.calc_qparams()
+        scale = (scale * mult).clone()
+        zp = zp.clone()
+        if "aff" in name:
+            zp = zp + 0.25  # learned (fractional) zero point: forward / backward use zero_point.round()
+        flat = x.reshape(-1)
+        s0 = float(scale.reshape(-1)[0])
+        flat[0], flat[1], flat[2] = 0.5 * s0, 1.5 * s0, -2.5 * s0  # exact rounding ties
+        gy = torch.randn(shape, generator=g)
+        scale_p = scale.clone().requires_grad_(True)
+        zp_r = zp.round().clone().requires_grad_(True)
+
+        class Ctx:
+            saved_tensors = (x, scale_p, zp_r)
+            qdesc = q.qdesc
+
+        with torch.no_grad():
+            gin, gs_e, gz_e, _, _ = MySTE.backward(Ctx, gy)
+        cases.append(name)
+        out[name + "_x"] = x.numpy()
+        out[name + "_gy"] = gy.numpy()
+        out[name + "_scale"] = scale.reshape(-1).numpy()
+        out[name + "_zp"] = zp.reshape(-1).numpy()
+        out[name + "_gx"] = gin.numpy()
+        out[name + "_gs_elem"] = gs_e.numpy()
+        out[name + "_gz_elem"] = gz_e.numpy()
+        out[name + "_meta"] = np.array([q.qdesc.qmin, q.qdesc.qmax, q.qdesc.ch_axis, int(q.qdesc.is_perchannel)])
+    out["cases"] = np.array(cases)
+    save("bwd", **out)
+
+
+GENERATORS = {"qdq": gen_qdq, "observers": gen_observers, "sparse": gen_sparse, "gptq": gen_gptq,
+              "next_rows": gen_next_rows, "calibration": gen_calibration, "bwd": gen_bwd}
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    gen_qdq()
-    gen_observers()
-    gen_sparse()
-    gen_gptq()
-    gen_next_rows()
-    gen_calibration()
+    for which in sys.argv[1:] or list(GENERATORS):  # e.g. `make_golden.py bwd` regenerates one fixture
+        GENERATORS[which]()

@@ -47,10 +47,38 @@ def test_perchannel_backward(shape, ch_axis):
     s = rng.uniform(0.01, 0.05, c).astype(np.float32)
     z = np.rint(rng.uniform(-3, 3, c)).astype(np.float32)
     st, zt = t(s).requires_grad_(True), t(z).requires_grad_(True)
+    # default: the reference per-channel kernel's zero-point rule (vq == qmax clipped, fake_quant_tensor.cu:264)
     gx, gs, gzp = fake_quant.quant_perchannel_backward(t(x), st, zt, t(gy), -16, 15, ch_axis, 0)
-    egx, egs, egz = oqdq.ste_backward(x, s, z, gy, -16, 15, ch_axis)
+    egx, egs, egz = oqdq.ste_backward(x, s, z, gy, -16, 15, ch_axis, gzp_open_top=True)
     assert bits_equal(gx.cpu().numpy(), egx)
     assert _rel(gs.cpu().numpy(), egs) < 1e-5 and _rel(gzp.cpu().numpy(), egz) < 1e-5
+    # extension flag: MySTE.backward's closed interval (quant_tensor.py:62-69)
+    gx2, gs2, gzp2 = fake_quant.quant_perchannel_backward(t(x), st, zt, t(gy), -16, 15, ch_axis, 0, gzp_closed=True)
+    _, _, egz2 = oqdq.ste_backward(x, s, z, gy, -16, 15, ch_axis)
+    assert torch.equal(gx, gx2) and torch.equal(gs, gs2)
+    assert _rel(gzp2.cpu().numpy(), egz2) < 1e-5
+    assert not np.allclose(egz, egz2)  # the two rules really differ on this data
+
+
+def test_backward_vs_reference_myste_golden(golden):
+    """tests/golden/bwd.npz = outputs of the reference's MySTE.backward (quant_tensor.py:46-71): gx bit-exact,
+    gs / gzp against the fp64 sums of its elementwise terms (per-channel: closed-interval flag)."""
+    g = golden("bwd")
+    for name in g["cases"]:
+        qmin, qmax, ch_axis, perch = (int(v) for v in g[name + "_meta"])
+        x, gy = g[name + "_x"], g[name + "_gy"]
+        st, zt = t(g[name + "_scale"]).requires_grad_(True), t(g[name + "_zp"]).requires_grad_(True)
+        if perch:
+            gx, gs, gzp = fake_quant.quant_perchannel_backward(t(x), st, zt, t(gy), qmin, qmax, ch_axis, 0, gzp_closed=True)
+            axes = tuple(a for a in range(x.ndim) if a != ch_axis)
+        else:
+            gx, gs, gzp = fake_quant.quant_pertensor_backward(t(x), st, zt, t(gy), qmin, qmax, 0)
+            axes = None
+        assert bits_equal(gx.cpu().numpy(), g[name + "_gx"]), name
+        for got, elem in ((gs, g[name + "_gs_elem"]), (gzp, g[name + "_gz_elem"])):
+            ref = elem.astype(np.float64).sum(axis=axes).reshape(-1)
+            l1 = np.abs(elem).astype(np.float64).sum(axis=axes).reshape(-1) + 1e-30
+            assert np.all(np.abs(got.cpu().numpy().reshape(-1) - ref) <= 1e-5 * l1), name
 
 
 def test_autograd_through_quantizer():

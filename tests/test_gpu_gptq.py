@@ -89,9 +89,17 @@ def test_tcgen05_path_vs_fp64_oracle(bshape, k, n, gs):
     finally:
         lib.sb200_gptq4_set_impl(0)
     exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, x.shape[:-1] + (n,)), scales, zeros, gs)
-    # same tolerance form as the reference's test, relative to each row's magnitude
-    rowmag = np.maximum(np.abs(exp).max(axis=-1, keepdims=True), 1.0)
-    np.testing.assert_array_less(np.abs(y - exp), 1e-5 + 1e-5 * rowmag * np.ones_like(exp))
+    yf, ef = y.reshape(-1, n), exp.reshape(-1, n)
+    # every ordinary row: the reference's own elementwise form, atol + rtol * |expected| (test_cuda_kernel.py:47)
+    plain = [r for r in range(yf.shape[0]) if r not in (0, 2)]
+    if plain:
+        np.testing.assert_allclose(yf[plain], ef[plain], **TOL)
+    # the two rows with injected outliers (|x| up to 7e4 next to 1e-6): an fp32 result cannot meet an elementwise
+    # bound against the fp64 oracle where the large terms cancel, so these rows are bounded by the row magnitude
+    for r in (0, 2):
+        if r < yf.shape[0]:
+            mag = max(np.abs(ef[r]).max(), 1.0)
+            np.testing.assert_array_less(np.abs(yf[r] - ef[r]), 1e-5 + 1e-5 * mag)
 
 
 @pytest.mark.parametrize("m,k,n", [(256, 1024, 512), (77, 512, 132)])

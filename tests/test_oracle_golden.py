@@ -250,3 +250,27 @@ def test_exact_division_schemes_on_cpu():
     out = json.loads(res.stdout)
     assert out["exact_trick_mismatches"] == 0 and out["fast_path_mismatches"] == 0
     assert out["cases"] > 5_000_000 and out["fast_path_accepted"] > 1_000_000
+
+
+def test_ste_backward_oracle_pinned_to_reference_myste(golden):
+    """oracle.qdq.ste_backward against outputs of the reference's MySTE.backward (quant_tensor.py:46-71,
+    generated by tests/golden/make_golden.py:gen_bwd): gx bit-exact; the scale / zero-point gradients equal the
+    fp64 sums of the reference's elementwise terms."""
+    from oracle import qdq as oqdq
+
+    g = golden("bwd")
+    for name in g["cases"]:
+        qmin, qmax, ch_axis, perch = (int(v) for v in g[name + "_meta"])
+        x, gy = g[name + "_x"], g[name + "_gy"]
+        gx, gs, gzp = oqdq.ste_backward(x, g[name + "_scale"], g[name + "_zp"], gy, qmin, qmax, ch_axis)
+        assert np.array_equal(gx, g[name + "_gx"]), name
+        axes = tuple(a for a in range(x.ndim) if a != ch_axis) if perch else None
+        ref_gs = g[name + "_gs_elem"].astype(np.float64).sum(axis=axes).reshape(-1)
+        ref_gz = g[name + "_gz_elem"].astype(np.float64).sum(axis=axes).reshape(-1)
+        l1s = np.abs(g[name + "_gs_elem"]).astype(np.float64).sum(axis=axes).reshape(-1) + 1e-30
+        l1z = np.abs(g[name + "_gz_elem"]).astype(np.float64).sum(axis=axes).reshape(-1) + 1e-30
+        assert np.all(np.abs(gs - ref_gs) <= 1e-6 * l1s), name
+        assert np.all(np.abs(gzp - ref_gz) <= 1e-6 * l1z), name
+        # the open-top rule only ever moves elements with vq == qmax into the clipped set
+        _, _, gzp_open = oqdq.ste_backward(x, g[name + "_scale"], g[name + "_zp"], gy, qmin, qmax, ch_axis, gzp_open_top=True)
+        assert gzp_open.shape == gzp.shape
