@@ -263,6 +263,20 @@ size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_si
 int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales,
                        const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                        int group_size, void* workspace, size_t workspace_bytes, void* stream);
+/* Per-call options instead of process-global switches.  impl: 0 = auto (M >= 128 -> 3, M >= 32 -> 2, else 1),
+ * 1 = SIMT, 2 = tcgen05 with exact int4 operands and a per-128-K-group fp32 rescale of the accumulator,
+ * 3 = tcgen05 with the scaled weights as two fp16 planes written to tensor memory (A operand) and whole-K
+ * accumulation, drained into fp32 registers every chunk_k K (multiple of 64; 0 = default 512) to bound the
+ * tensor core's truncating accumulation. */
+typedef struct sb200_gptq4_options {
+  int impl;
+  int chunk_k;
+  int reserved[6]; /* must be zero */
+} sb200_gptq4_options;
+int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, const float* scales,
+                          const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
+                          int group_size, const sb200_gptq4_options* options, void* workspace,
+                          size_t workspace_bytes, void* stream);
 /* Any bit width of the reference's module: bits = 4 forwards to sb200_gptq4_matmul; bits = 3 / 2
  * replace vecquant3matmul / vecgroupquant3matmul / vecquant2matmul / vecgroupquant2matmul
  * (cuda_kernel.cpp:26-57,68-72; cuda_kernel_3bit.cu, cuda_kernel_2bit.cu).  Packed layouts of
@@ -272,7 +286,8 @@ int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const
 int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const float* scales,
                       const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                       int bits, int group_size, void* workspace, size_t workspace_bytes, void* stream);
-/* Force a GPTQ implementation: 0 = auto, 1 = SIMT, 2 = tcgen05.  For tests / benchmarking. */
+/* Force a GPTQ implementation for sb200_gptq4_matmul (process-wide; tests / benchmarking only -- prefer the
+ * per-call sb200_gptq4_matmul_ex): 0 = auto, 1 = SIMT, 2 / 3 = the two tcgen05 kernels. */
 int sb200_gptq4_set_impl(int impl);
 
 /* Tuning knob of the tcgen05 kernel: nanoseconds its mostly-waiting roles (TMA producer, MMA issuer waiting for a

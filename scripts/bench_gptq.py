@@ -20,6 +20,7 @@ from sparsebit_b200 import _lib, ops
 dev = torch.device("cuda:0")
 SHAPES = [("qkvo", 4096, 4096, 4), ("gate_up", 4096, 11008, 2), ("down", 11008, 4096, 1)]  # name, K, N, count per layer
 LAYERS = 32
+TS_CHUNKS = [int(c) for c in os.environ.get("SB200_TS_CHUNKS", "512").split(",")]
 
 
 def load_ref():
@@ -89,16 +90,16 @@ def run(ms, with_reference=True, quiet=False):
                 # the reference's model path: fp16 activations cast to fp32 (utils/quant.py:262-277)
                 x = x.half().float()
             y = torch.zeros(m, n, device=dev)
-            impls = [("ours_auto", 0)] + ([("ours_simt", 1)] if m <= 64 else []) + [("ours_tcgen05", 2)]
-            for label, impl in impls:
-                lib.sb200_gptq4_set_impl(impl)
+            impls = [("ours_auto", 0, 0)] + ([("ours_simt", 1, 0)] if m <= 64 else []) + [("ours_tcgen05_group", 2, 0)]
+            if m >= 32:  # the tensor-memory-operand kernel, accumulator drained every chunk_k K
+                impls += [(f"ours_tcgen05_ts_c{c}", 3, c) for c in TS_CHUNKS]
+            for label, impl, chunk in impls:
                 try:
-                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128), 20 if m > 64 else 200, copies)
+                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128, impl=impl, chunk_k=chunk),
+                               20 if m > 64 else 200, copies)
                 except RuntimeError as e:
                     emit({"shape": name, "M": m, "impl": label, "error": str(e)[:100]})
                     continue
-                finally:
-                    lib.sb200_gptq4_set_impl(0)
                 emit({"shape": name, "K": k, "N": n, "M": m, "impl": label, "acts": "fp16->fp32" if fp16_acts else "fp32",
                       "us": t * 1e6, "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9})
                 totals[(m, label)] = totals.get((m, label), 0.0) + t * cnt * LAYERS
@@ -114,7 +115,7 @@ def run(ms, with_reference=True, quiet=False):
 
 def main():
     ms = [int(a) for a in sys.argv[1:]] or [1, 16, 2048]
-    totals = run(ms)
+    totals = run(ms, with_reference=os.environ.get("SB200_NO_REF", "0") != "1")
     for (m, label), t in sorted(totals.items()):
         print(json.dumps({"summary": "llama7b_all_linears", "M": m, "impl": label, "ms_per_forward": t * 1e3, "tok_per_s": m / t}))
 

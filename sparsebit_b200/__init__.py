@@ -33,6 +33,17 @@ def install():
 
     for name in ("minmax", "mse", "percentile", "kl_histogram", "moving_average", "aciq"):
         ref_obs.OBSERVERS_MAP[name] = my_obs.OBSERVERS_MAP[name]
+    # The reference's own LSQ / LSQ+ quantizers stay in place and read the calibration batches themselves
+    # (data_cache.get_data_for_calibration, lsq.py:36, lsq_plus.py:26): their observers must retain the batches.
+    for modname in ("lsq", "lsq_plus"):
+        cls = importlib.import_module(f"sparsebit.quantization.quantizers.{modname}").Quantizer
+        if not getattr(cls, "_sb200_keep_data", False):
+            def _init(self, config, _orig=cls.__init__):
+                _orig(self, config)
+                self.observer.keep_data = True
+
+            cls.__init__ = _init
+            cls._sb200_keep_data = True
     # QuantModel.prepare_calibration imports CalibrationRunner at call time (quant_model.py:185-189)
     ref_cal = importlib.import_module("sparsebit.quantization.tools.calibration")
     from .quantization.tools import CalibrationRunner

@@ -46,6 +46,20 @@ extern int g_variant;
     }                                                                                     \
   } while (0)
 
+// Per-device one-time cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute is per device, so a process
+// driving several GPUs must set it on each (a process-wide `static bool` would skip the second device).
+template <typename KernelT>
+static inline cudaError_t ensure_dyn_smem(KernelT kernel, int bytes, std::atomic<int>* done_per_device /*[64]*/) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (done_per_device[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done_per_device[dev].store(bytes, std::memory_order_release);
+  return e;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------- order-preserving float key

@@ -14,6 +14,10 @@ size_t gptq4_tc_workspace(long long M, long long K, long long N, int group_size)
 int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
              long long K, long long N, long long KW, int group_size, void* workspace, size_t workspace_bytes,
              cudaStream_t st);
+size_t gptq4_ts_workspace(long long M, long long K, long long N, int group_size);
+int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
+             long long K, long long N, long long KW, int group_size, int chunk_kb, void* workspace, size_t workspace_bytes,
+             cudaStream_t st);
 void gptq4_tc_set_trace(long long* p);
 void gptq4_tc_set_backoff(int ns);
 int gptq_lowbit(int bits, const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
@@ -26,7 +30,7 @@ using namespace sb200;
 extern "C" {
 
 int sb200_gptq4_set_impl(int impl) {
-  SB_REQUIRE(impl >= 0 && impl <= 2, "sb200_gptq4_set_impl: impl must be 0, 1 or 2 (got %d)", impl);
+  SB_REQUIRE(impl >= 0 && impl <= 3, "sb200_gptq4_set_impl: impl must be 0, 1, 2 or 3 (got %d)", impl);
   g_gptq_impl = impl;
   return SB200_OK;
 }
@@ -45,12 +49,13 @@ int sb200_gptq4_set_trace(int64_t* device_buffer) {
 size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size) {
   if (m <= 0 || k <= 0 || n <= 0) return 0;
   if (group_size <= 0) group_size = (int)k;
-  return gptq4_tc_workspace(m, k, n, group_size);
+  const size_t a = gptq4_tc_workspace(m, k, n, group_size), b = gptq4_ts_workspace(m, k, n, group_size);
+  return a > b ? a : b;
 }
 
-int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
-                       int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+                          int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size, int impl, int chunk_k,
+                          void* workspace, size_t workspace_bytes, void* stream) {
   SB_REQUIRE(x && qweight && out && scales && zeros, "sb200_gptq4_matmul: null pointer argument");
   SB_REQUIRE(m > 0 && k > 0 && n > 0, "sb200_gptq4_matmul: empty operand (M=%lld K=%lld N=%lld)", (long long)m,
              (long long)k, (long long)n);
@@ -58,6 +63,8 @@ int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const
   SB_REQUIRE(qweight_rows >= (k + 7) / 8,
              "sb200_gptq4_matmul: qweight has %lld rows, need ceil(K/8) = %lld", (long long)qweight_rows,
              (long long)((k + 7) / 8));
+  SB_REQUIRE(impl >= 0 && impl <= 3, "sb200_gptq4_matmul: impl must be 0 (auto), 1 (SIMT), 2 or 3 (tcgen05) (got %d)", impl);
+  SB_REQUIRE(chunk_k >= 0 && chunk_k % 64 == 0, "sb200_gptq4_matmul: chunk_k must be a multiple of 64 (got %d)", chunk_k);
   if (group_size != 0) {
     // cuda_kernel_4bit.cu:60
     SB_REQUIRE(group_size > 0 && group_size % 128 == 0,
@@ -66,24 +73,47 @@ int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const
     group_size = (int)k;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  bool use_tc = false;
-  if (g_gptq_impl != 1) {
-    const bool ok = gptq4_tc_supported(x, qweight, out, m, k, n, qweight_rows, group_size) &&
-                    workspace && workspace_bytes >= gptq4_tc_workspace(m, k, n, group_size);
-    if (g_gptq_impl == 2) {
-      if (!ok) {
+  // 1 = SIMT (any shape);  2 = tcgen05, exact int4 operands + per-128-K-group fp32 rescale (gptq_tc.cu);
+  // 3 = tcgen05, scaled fp16 weight planes written to tensor memory, whole-K accumulation (gptq_ts.cu).
+  int use = 1;
+  if (impl != 1) {
+    const bool shape_ok = gptq4_tc_supported(x, qweight, out, m, k, n, qweight_rows, group_size) && workspace;
+    const bool ok2 = shape_ok && workspace_bytes >= gptq4_tc_workspace(m, k, n, group_size);
+    const bool ok3 = shape_ok && workspace_bytes >= gptq4_ts_workspace(m, k, n, group_size);
+    if (impl == 2 || impl == 3) {
+      if (!(impl == 2 ? ok2 : ok3)) {
         set_error("sb200_gptq4_matmul: tcgen05 path forced but shape/workspace unsupported (M=%lld K=%lld N=%lld gs=%d ws=%zu)",
                   (long long)m, (long long)k, (long long)n, group_size, workspace_bytes);
         return SB200_E_UNSUPPORTED;
       }
-      use_tc = true;
-    } else {
-      use_tc = ok && m >= 32;
+      use = impl;
+    } else if (ok3 && m >= 128) {
+      use = 3;
+    } else if (ok2 && m >= 32) {
+      use = 2;
     }
   }
-  if (use_tc)
+  if (use == 3)
+    return gptq4_ts(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, chunk_k / 64, workspace,
+                    workspace_bytes, st);
+  if (use == 2)
     return gptq4_tc(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, workspace, workspace_bytes, st);
   return gptq4_simt(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
+}
+
+int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+                       int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return gptq4_dispatch(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, g_gptq_impl, 0, workspace,
+                        workspace_bytes, stream);
+}
+
+int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
+                          int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size,
+                          const sb200_gptq4_options* options, void* workspace, size_t workspace_bytes, void* stream) {
+  const int impl = options ? options->impl : 0, chunk_k = options ? options->chunk_k : 0;
+  return gptq4_dispatch(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, impl, chunk_k, workspace,
+                        workspace_bytes, stream);
 }
 
 int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,

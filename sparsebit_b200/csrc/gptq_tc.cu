@@ -33,12 +33,7 @@
 // warps draining; TMEM read bandwidth is 64 B/clk = 1024 cycles per group at best), the unpack ~670 per stage.
 //   warp 2      TMEM allocator.
 // A prologue kernel splits x into (hi, lo), computes the per-(row, 128-K) sums and the row scales.
-#include <cuda.h>
-#include <cuda_fp16.h>
-
-#include <mutex>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sb200 {
 
@@ -71,108 +66,6 @@ struct TcSmem {
   alignas(16) float scw[8][2][64];
   alignas(16) float zrw[8][2][64];
 };
-
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accum)
-      : "memory");
-}
-// mbarrier wait with an optional back-off between polls: the producer / issuer / unpack roles spend most of their
-// time waiting, and every poll is an MIO operation competing with the LDS / STS / tcgen05.ld traffic of the
-// roles that are busy (sb200_gptq4_set_wait_backoff; 0 = poll continuously like mbar_wait).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int backoff_ns) {
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (backoff_ns > 0) __nanosleep((unsigned)backoff_ns);
-  }
-}
-// elect.sync: exactly one lane of a converged warp gets `true`.  Unlike `lane == 0` the compiler knows the
-// guarded code runs on a single lane of a uniform warp and keeps tcgen05 operands in uniform registers
-// (no per-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY lane loop).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, %1;\n\t"
-      "@px mov.s32 %0, 1;\n\t}"
-      : "+r"(pred)
-      : "r"(0xFFFFFFFFu));
-  return pred != 0;
-}
-template <uint32_t MASK>
-__device__ __forceinline__ uint32_t and_or(uint32_t x, uint32_t c) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "n"(MASK), "r"(c));
-  return r;
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-      "%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-// wait for the outstanding tcgen05.ld; the registers are threaded through the statement so that no use of them
-// can be scheduled above the wait
-__device__ __forceinline__ void tc_wait_ld16(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-
-// Register re-balancing between warpgroups (the kernel is launched with 65536 / 640 -> 96 registers per
-// thread; the epilogue needs ~130 for its 64 accumulators, the other roles far fewer).
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major) | [32,46) SBO >> 4 = 1024 B
@@ -556,15 +449,25 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const float rs = __ldg(rowscale + m);
       float* orow = out + (size_t)m * N + n0 + col0;
       if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
+        // four independent 128-bit loads in flight, then four stores (a load-modify-store per float4 would be
+        // 16 serialised global round trips: the compiler cannot reorder a load above the previous store)
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-          if (n0 + col0 + 4 * j4 < N) {
-            float4 o = *reinterpret_cast<float4*>(orow + 4 * j4);
-            o.x = fmaf(rs, acc[4 * j4 + 0], o.x);
-            o.y = fmaf(rs, acc[4 * j4 + 1], o.y);
-            o.z = fmaf(rs, acc[4 * j4 + 2], o.z);
-            o.w = fmaf(rs, acc[4 * j4 + 3], o.w);
-            *reinterpret_cast<float4*>(orow + 4 * j4) = o;
+        for (int b4 = 0; b4 < 16; b4 += 4) {
+          float4 o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[i] = (n0 + col0 + 4 * (b4 + i) < N) ? __ldcg(reinterpret_cast<const float4*>(orow + 4 * (b4 + i)))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j4 = b4 + i;
+            if (n0 + col0 + 4 * j4 < N) {
+              o[i].x = fmaf(rs, acc[4 * j4 + 0], o[i].x);
+              o[i].y = fmaf(rs, acc[4 * j4 + 1], o[i].y);
+              o[i].z = fmaf(rs, acc[4 * j4 + 2], o[i].z);
+              o[i].w = fmaf(rs, acc[4 * j4 + 3], o[i].w);
+              __stcg(reinterpret_cast<float4*>(orow + 4 * j4), o[i]);
+            }
           }
         }
       } else {
@@ -583,37 +486,6 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-static bool make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
-                        uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
-  const cuuint64_t dims[2] = {inner, outer};
-  const cuuint64_t strides[1] = {row_bytes};
-  const cuuint32_t box[2] = {box_inner, box_outer};
-  const cuuint32_t estr[2] = {1, 1};
-  return enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
 struct TcWorkspace {
   size_t off_hi, off_lo, off_xsum, off_rs, off_zint, off_flag, total;
 };
@@ -628,6 +500,13 @@ static TcWorkspace tc_layout(long long M, long long K, long long N = 0, long lon
   w.off_flag = w.off_zint + align_up((size_t)N * Gq * 2, 1024);
   w.total = w.off_flag + 1024;
   return w;
+}
+
+int gptq_launch_split(const float* x, __half* a_hi, __half* a_lo, float* xsum, float* rowscale, int* need_lo, long long M,
+                      int K, int G, cudaStream_t st) {
+  gptq_split_kernel<<<(unsigned)M, 256, 0, st>>>(x, a_hi, a_lo, xsum, rowscale, need_lo, K, G);
+  SB_LAUNCHED();
+  return SB200_OK;
 }
 
 static long long* g_tc_trace = nullptr;
@@ -689,11 +568,8 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
     return SB200_E_CUDA;
   }
   const size_t smem = (size_t)kStages * kStageBytes + sizeof(TcSmem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SB_CUDA(cudaFuncSetAttribute(gptq4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  static std::atomic<int> attr_done[64];
+  SB_CUDA(ensure_dyn_smem(gptq4_tc_kernel, (int)smem, attr_done));
   const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)((N + kTileN - 1) / kTileN));
   gptq4_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_hi, map_lo, map_q, out, scales, zeros, xsum, rowscale, zint, flag,
                                                   (int)M, (int)K, (int)N, Gq, G128, group_size, g_tc_trace,

@@ -659,11 +659,8 @@ int sb200_observe_minmax_perchannel(const float* x, int64_t outer, int64_t chann
   } else if (inner <= 64) {
     const long long ctas = (rows + 32 * (kThreads / 32) - 1) / (32 * (kThreads / 32));
     const size_t smem = (size_t)(kThreads / 32) * 32 * inner * sizeof(float);  // <= 64 KB
-    static bool attr_done = false;
-    if (!attr_done) {
-      SB_CUDA(cudaFuncSetAttribute(minmax_rows_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr_done = true;
-    }
+    static std::atomic<int> attr_done[64];  // per device
+    SB_CUDA(ensure_dyn_smem(minmax_rows_tiny_kernel, 64 * 1024, attr_done));
     minmax_rows_tiny_kernel<<<persistent_grid(ctas, 3), kThreads, smem, st>>>(x, rows, (int)inner, (int)channels, state);
   } else {
     const long long ctas = (rows + 4 * (kThreads / 32) - 1) / (4 * (kThreads / 32));

@@ -325,17 +325,13 @@ template <bool STATS>
 static int launch_stream_tma(const float* x, float* out, const float* scale, const float* zp, long long n, int qmin,
                              int qmax, int rounding, uint32_t* mm, cudaStream_t st) {
   const size_t smem = (size_t)kTmaStages * kTmaTile * sizeof(float);
-  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  static std::atomic<int> attr_done[2][64];  // [rounding variant][device]
   const long long ntiles = ((n & ~3LL) + kTmaTile - 1) / kTmaTile;
   long long grid = (long long)sm_count() * kTmaCtasPerSm;
   if (grid > ntiles) grid = ntiles < 1 ? 1 : ntiles;
 #define SB_GO(R_)                                                                                              \
   do {                                                                                                         \
-    if (!attr_done[STATS ? 1 : 0][R_ == 0 ? 0 : 1]) {                                                          \
-      SB_CUDA(cudaFuncSetAttribute(stream_tma_kernel<STATS, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                   (int)smem));                                                                \
-      attr_done[STATS ? 1 : 0][R_ == 0 ? 0 : 1] = true;                                                        \
-    }                                                                                                          \
+    SB_CUDA(ensure_dyn_smem(stream_tma_kernel<STATS, R_>, (int)smem, attr_done[R_ == 0 ? 0 : 1]));            \
     stream_tma_kernel<STATS, R_><<<(unsigned)grid, kThreads, smem, st>>>(x, out, scale, zp, n, (float)qmin,    \
                                                                          (float)qmax, rounding, mm);           \
   } while (0)

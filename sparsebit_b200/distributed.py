@@ -2,22 +2,33 @@
 
 The reference has no such path (every rank calibrates redundantly); here the
 calibration set is split by sample across ranks and the *statistics* -- never the activations --
-cross NVLink:
-  round 1  MAX   all-reduce over packed {max_key, -min_key} of EVERY observer (order-preserving
-                 integer keys -> bit-exact regardless of reduction order)
-  round 2  SUM   all-reduce over packed int64 histograms / fp64 SSE sums / counts
-Messages are KB-sized, i.e. latency-bound: what matters is ONE collective per round for all
-quantizers, which ``sync_minmax`` / ``sync_sum`` provide by packing into a flat buffer.
+cross NVLink.  Messages are KB-sized, i.e. latency-bound: what matters is the NUMBER of collectives,
+so the observers do not call torch.distributed themselves.  Their ``calc_qparams`` is written as a
+generator (``calc_qparams_steps``) that *yields* what it needs merged:
+
+    Sync.max(states)    running min/max states (order-preserving integer keys): one MAX all-reduce over
+                        {max_key, -min_key} -- bit-exact for any rank count and reduction order
+    Sync.sum(tensors)   int64 histograms / counts, fp64 moment and squared-error sums: one SUM all-reduce
+                        (everything travels as fp64; counts are exact below 2^53)
+    Sync.gather(tensor) per-sample statistics whose order matters (MovingAverage): one all-gather
+
+``drive(gen)`` runs ONE observer and performs each request on its own.  ``drive_all(gens)`` advances
+EVERY quantizer of a model in lockstep and packs the requests of a round into ONE MAX, ONE SUM (and one
+all-gather, if any MovingAverage observer is present): a whole model calibrates with 2 collectives
+(MinMax / MSE / KL / ACIQ) or 4 (Percentile: three radix-select passes).  Statistics of WEIGHT quantizers
+are replicated on every rank and are never merged (a SUM would multiply their counts by the world size).
+``collectives()`` counts what was issued, for tests and ``bench.py``.
 """
 import torch
 import torch.distributed as dist
 
 _group = None
 _enabled = False
+_issued = {"max": 0, "sum": 0, "gather": 0}
 
 
 def enable(group=None):
-    """Turn on statistic all-reduces inside the observers (torch.distributed must be initialised)."""
+    """Turn on statistic merging inside the observers (torch.distributed must be initialised)."""
     global _group, _enabled
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
@@ -33,6 +44,37 @@ def active():
     return _enabled and dist.is_initialized() and dist.get_world_size(_group) > 1
 
 
+def collectives(reset=False):
+    """{'max': n, 'sum': n, 'gather': n} collectives issued since the last reset."""
+    out = dict(_issued)
+    if reset:
+        for k in _issued:
+            _issued[k] = 0
+    return out
+
+
+class Sync:
+    """One merge request of an observer step.  ``local=True`` (weight statistics) is never communicated."""
+
+    __slots__ = ("kind", "tensors", "local", "result")
+
+    def __init__(self, kind, tensors, local=False):
+        self.kind, self.tensors, self.local, self.result = kind, list(tensors), local, None
+
+    @classmethod
+    def max(cls, states, local=False):
+        return cls("max", states, local)
+
+    @classmethod
+    def sum(cls, tensors, local=False):
+        return cls("sum", tensors, local)
+
+    @classmethod
+    def gather(cls, tensor, local=False):
+        return cls("gather", [tensor], local)
+
+
+# ----------------------------------------------------------------------------- packing helpers
 def _keys_from_state(state):
     """int32 minmax state (bit patterns of uint32 keys) -> int64 keys, layout [.., (min, max)]."""
     return state.to(torch.int64) & 0xFFFFFFFF
@@ -55,8 +97,7 @@ def unpack_minmax(packed, states):
     for s in states:
         n = s.numel()
         k = keys[off : off + n]
-        # back to the int32 bit pattern
-        s.copy_(torch.where(k >= 2**31, k - 2**32, k).to(torch.int32))
+        s.copy_(torch.where(k >= 2**31, k - 2**32, k).to(torch.int32))  # back to the int32 bit pattern
         off += n
 
 
@@ -66,17 +107,88 @@ def sync_minmax(states):
         return
     packed = pack_minmax(states)
     dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=_group)
+    _issued["max"] += 1
     unpack_minmax(packed, states)
 
 
 def sync_sum(tensors):
-    """In-place SUM across ranks of several tensors of one dtype: ONE all-reduce."""
+    """In-place SUM across ranks of several int64 / float tensors: ONE all-reduce (as fp64)."""
     if not active() or not tensors:
         return
-    flat = torch.cat([t.reshape(-1) for t in tensors])
+    flat = torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_group)
+    _issued["sum"] += 1
     off = 0
     for t in tensors:
         n = t.numel()
-        t.copy_(flat[off : off + n].view_as(t))
+        part = flat[off : off + n].view_as(t)
+        t.copy_(part.round().to(t.dtype) if not t.dtype.is_floating_point else part.to(t.dtype))
         off += n
+
+
+def gather_cat(tensors):
+    """All-gather several tensors (same shapes on every rank) with ONE collective; returns, per input, the
+    list of its per-rank copies in rank order."""
+    if not active():
+        return [[t] for t in tensors]
+    world = dist.get_world_size(_group)
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat, group=_group)
+    _issued["gather"] += 1
+    out, off = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append([p[off : off + n].view_as(t).to(t.dtype) for p in parts])
+        off += n
+    return out
+
+
+# ----------------------------------------------------------------------------- drivers
+def _serve(requests):
+    """Perform the requests of one round with at most one collective per kind."""
+    live = [r for r in requests if r is not None and not r.local]
+    if active():
+        sync_minmax([s for r in live if r.kind == "max" for s in r.tensors])
+        sync_sum([t for r in live if r.kind == "sum" for t in r.tensors])
+        gathers = [r for r in live if r.kind == "gather"]
+        if gathers:
+            for r, parts in zip(gathers, gather_cat([r.tensors[0] for r in gathers])):
+                r.result = parts
+    for r in requests:
+        if r is not None and r.kind == "gather" and r.result is None:
+            r.result = [r.tensors[0]]
+
+
+def drive(gen):
+    """Run one ``*_steps`` generator to completion, serving each request on its own; returns its value."""
+    try:
+        req = next(gen)
+        while True:
+            _serve([req])
+            req = gen.send(req.result)
+    except StopIteration as stop:
+        return stop.value
+
+
+def drive_all(gens):
+    """Advance all generators in lockstep: every round's requests are packed into one collective per kind.
+    Every rank must pass the same quantizers in the same order.  Returns the generators' values."""
+    gens = list(gens)
+    results = [None] * len(gens)
+    pending = {}
+    for i, g in enumerate(gens):
+        try:
+            pending[i] = next(g)
+        except StopIteration as stop:
+            results[i] = stop.value
+    while pending:
+        _serve(list(pending.values()))
+        nxt = {}
+        for i, req in pending.items():
+            try:
+                nxt[i] = gens[i].send(req.result)
+            except StopIteration as stop:
+                results[i] = stop.value
+        pending = nxt
+    return results

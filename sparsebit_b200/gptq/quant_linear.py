@@ -91,7 +91,9 @@ class QuantMatmul(torch.autograd.Function):
         was_cuda = input.is_cuda
         dev = input.device if was_cuda else torch.device("cuda")
         x = input.to(dev).contiguous()
-        y = bias.to(device=dev, dtype=x.dtype).expand(lead + [bias.numel()]).contiguous()
+        # a private copy (the reference uses .repeat): expand(...).contiguous() of a [1, N] view would alias the
+        # bias buffer itself and the in-place accumulation below would corrupt it
+        y = bias.to(device=dev, dtype=x.dtype).expand(lead + [bias.numel()]).clone(memory_format=torch.contiguous_format)
         plain = {2: cuda_kernel.vecquant2matmul, 3: cuda_kernel.vecquant3matmul, 4: cuda_kernel.vecquant4matmul}[bit]
         grouped = {2: cuda_kernel.vecgroupquant2matmul, 3: cuda_kernel.vecgroupquant3matmul,
                    4: cuda_kernel.vecgroupquant4matmul}[bit]

@@ -4,6 +4,8 @@ Every function takes CUDA fp32 tensors, launches on ``torch.cuda.current_stream(
 tensor's device and never synchronises the host.  Non-fp32 / empty / CPU inputs raise
 ``RuntimeError`` like the reference's pybind modules do (torch_extensions/common.cuh:45-55).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -350,8 +352,13 @@ def mask_apply_qdq_perchannel(w, mask, scale, zero_point, qmin, qmax, ch_axis=0,
 _gptq_ws = {}
 
 
-def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0):
-    """In-place ``out += x @ dequant(qweight)`` (vecquant4matmul contract, cuda_kernel.cpp:10-23)."""
+class _Gptq4Options(ctypes.Structure):  # include/sparsebit_b200.h sb200_gptq4_options
+    _fields_ = [("impl", ctypes.c_int), ("chunk_k", ctypes.c_int), ("reserved", ctypes.c_int * 6)]
+
+
+def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0, impl=None, chunk_k=0):
+    """In-place ``out += x @ dequant(qweight)`` (vecquant4matmul contract, cuda_kernel.cpp:10-23).
+    ``impl`` / ``chunk_k``: per-call kernel selection (sb200_gptq4_matmul_ex); None = the library default."""
     lib = _lib.load()
     _req(x, "inp1"), _req(out, "out"), _req(scales, "scales"), _req(zeros, "zeros")
     _req(qweight, "inp2", torch.int32)
@@ -373,9 +380,15 @@ def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             _gptq_ws[key] = ws
     with torch.cuda.device(x.device):
-        check(lib.sb200_gptq4_matmul(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(), zeros.data_ptr(),
-                                     m, k, n, qweight.shape[0], int(group_size), ws.data_ptr() if ws is not None else None,
-                                     ws_bytes, _stream(x)))
+        if impl is None and not chunk_k:
+            check(lib.sb200_gptq4_matmul(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(), zeros.data_ptr(),
+                                         m, k, n, qweight.shape[0], int(group_size), ws.data_ptr() if ws is not None else None,
+                                         ws_bytes, _stream(x)))
+        else:
+            opts = _Gptq4Options(int(impl or 0), int(chunk_k))
+            check(lib.sb200_gptq4_matmul_ex(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(),
+                                            zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size), ctypes.byref(opts),
+                                            ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x)))
     return out
 
 

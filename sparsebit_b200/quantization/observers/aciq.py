@@ -10,6 +10,7 @@ import math
 
 import torch
 
+from ... import distributed as sbdist
 from ... import ops
 from ..common import QuantTarget
 from . import Observer as BaseObserver
@@ -41,8 +42,12 @@ class Observer(BaseObserver):
         affine = self.qdesc.scheme in (torch.per_channel_affine, torch.per_tensor_affine)
         return affine and bool(min_all >= 0)
 
-    def calc_minmax(self):
-        mn, mx = self._running_minmax()
+    def _reset_state(self):
+        super()._reset_state()
+        self._numel = 0
+
+    def calc_minmax_steps(self):
+        mn, mx = yield from self._running_minmax_steps()  # round 1: MAX
         mn, mx = mn.cpu(), mx.cpu()
         half = self._affine_half_range(mn.min())
         bit = self.qdesc.bit
@@ -54,14 +59,16 @@ class Observer(BaseObserver):
             spread = (ALPHA_GAUS_POSITIVE if half else ALPHA_GAUS)[bit] * std
         else:
             rows = self.data_cache.rows(self.is_perchannel)
-            count = sum(r.shape[1] for r in rows)
+            count = torch.tensor([float(sum(r.shape[1] for r in rows))], dtype=torch.float64, device=rows[0].device)
             first = ops.moments_new(rows[0].shape[0], rows[0].device)
             for r in rows:
                 ops.moments_update(r, first)
+            yield sbdist.Sync.sum([first, count], local=self._local)  # round 2: SUM -> the mean of the WHOLE set
             mean = (first[:, 0] / count).contiguous()
             second = ops.moments_new(rows[0].shape[0], rows[0].device)
             for r in rows:
                 ops.moments_update(r, second, centre=mean)
+            yield sbdist.Sync.sum([second], local=self._local)  # round 3: SUM of |x - mean|
             b = (second[:, 3] / count).to(torch.float32).cpu()
             if not self.is_perchannel:
                 b = b.reshape(())

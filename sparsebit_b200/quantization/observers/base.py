@@ -30,6 +30,7 @@ class DataCache:
 
     def update(self, data):
         x = data.detach()
+        src_ptr = x.data_ptr() if x.is_cuda else None
         if not x.is_cuda:
             if not torch.cuda.is_available():
                 raise ops.SparsebitB200Error("sparsebit_b200 observers need a CUDA device (no CPU fallback)")
@@ -43,14 +44,45 @@ class DataCache:
         if self.qdesc.bs_axis is not None:
             self._batch_size += x.shape[self.qdesc.bs_axis]
         if self._owner is None or getattr(self._owner, "keep_data", self._owner.KEEP_DATA):
+            # a retained batch must not alias the caller's tensor: the streaming pre-hook hands over the live
+            # activation, which an in-place operator (ReLU(inplace=True), the torchvision default) overwrites
+            # before the observer's second pass.  (The reference is immune because it copies to the CPU.)
+            if src_ptr is not None and x.data_ptr() == src_ptr:
+                x = x.clone()
             self._tensors.append(x)
         if self._owner is not None:
             self._owner._ingest(x)
 
     def reset(self):
+        """The reference idiom ``observer.data_cache.reset()`` (tools/calibration.py:113) drops everything the
+        observer accumulated -- here that includes the owner's streaming state (running min/max, per-sample
+        extrema, element counts), so a later calibration never merges with stale statistics."""
         self._tensors = []
         self._batches = 0
         self._batch_size = 0
+        if self._owner is not None:
+            self._owner._reset_state()
+
+    def release(self):
+        """Drop the retained batches only (the owner's streaming state stays): what ``calc_qparams`` does
+        before ``calc_qparams_with_minmax`` asserts an empty cache (observers/base.py:78, Q10)."""
+        self._tensors = []
+        self._batches = 0
+
+    def get_data_for_calibration(self, granularity):
+        """Reference API (observers/base.py:22-36), kept for the reference's own LSQ / LSQ+ quantizers under
+        ``install()``: the cached batches as ONE tensor -- flat for layer-wise statistics, [C, M] channel-first
+        for channel-wise ones.  Needs an observer that retains its batches (``keep_data``)."""
+        kind = getattr(granularity, "name", str(granularity)).split(".")[-1].upper()  # ours or the reference's enum
+        assert kind in ("LAYERWISE", "CHANNELWISE"), "only layerwise or channelwise quantization are supported now!"
+        assert self._batches, "No data cached!"
+        if not self._tensors:
+            raise ops.SparsebitB200Error(
+                "get_data_for_calibration: this observer streams its statistics and keeps no batches; set "
+                "observer.keep_data = True before calibration (sparsebit_b200.install() does it for LSQ / LSQ+)")
+        if kind == "LAYERWISE":
+            return torch.cat([t.reshape(-1) for t in self._tensors], dim=0)
+        return torch.cat(self.rows(True), dim=1)
 
     def __len__(self):
         return self._batches
@@ -102,25 +134,46 @@ class Observer(nn.Module):
             self._mm_state = ops.minmax_new(c, x.device)
         ops.minmax_update(x, self._mm_state, self.qdesc.ch_axis if self.is_perchannel else None)
 
-    def _running_minmax(self):
+    @property
+    def _local(self):
+        """Weight statistics are replicated on every rank: never merged across ranks."""
+        return self.qdesc.target == QuantTarget.WEIGHT
+
+    def _running_minmax_steps(self):
         assert self._mm_state is not None, "No data cached!"
-        sbdist.sync_minmax([self._mm_state])
+        yield sbdist.Sync.max([self._mm_state], local=self._local)
         mn, mx = ops.minmax_read(self._mm_state)
         if not self.is_perchannel:
             mn, mx = mn.reshape(()), mx.reshape(())
         return mn, mx
 
-    def _reset(self):
-        self.data_cache.reset()
+    def _running_minmax(self):
+        return sbdist.drive(self._running_minmax_steps())
+
+    def _reset_state(self):
+        """Drop the streaming state (called by ``data_cache.reset()``); subclasses extend."""
         self._mm_state = None
 
+    def _reset(self):
+        self.data_cache.reset()
+
     # ---- reference interface -----------------------------------------------------------------
-    def calc_minmax(self):
+    # Every observer states its reduction as a generator (``*_steps``) that yields the statistics to merge across
+    # ranks (sparsebit_b200.distributed.Sync); ``calc_minmax`` / ``calc_qparams`` drive it stand-alone, the
+    # CalibrationRunner drives all quantizers of a model in lockstep with packed collectives.
+    def calc_minmax_steps(self):
         raise NotImplementedError
+        yield  # pragma: no cover
+
+    def calc_minmax(self):
+        return sbdist.drive(self.calc_minmax_steps())
+
+    def calc_qparams_steps(self):
+        min_val, max_val = yield from self.calc_minmax_steps()
+        return self.calc_qparams_with_minmax(min_val, max_val)
 
     def calc_qparams(self):
-        min_val, max_val = self.calc_minmax()
-        return self.calc_qparams_with_minmax(min_val, max_val)
+        return sbdist.drive(self.calc_qparams_steps())
 
     def calc_qparams_with_minmax(self, min_val, max_val):
         """observers/base.py:63-79, same fp32 torch ops on tiny tensors (not the hot path)."""

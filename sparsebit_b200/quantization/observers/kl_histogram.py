@@ -125,10 +125,10 @@ class Observer(BaseObserver):
         super().__init__(config, qdesc)
         self.bins = 2048
 
-    def calc_minmax(self):
+    def calc_minmax_steps(self):
         rows = self.data_cache.rows(self.is_perchannel)
-        mn, mx = self._running_minmax()
-        self.data_cache.reset()
+        mn, mx = yield from self._running_minmax_steps()  # round 1: MAX
+        self.data_cache.release()
         dev = rows[0].device
         nrows = rows[0].shape[0]
         mn, mx = mn.reshape(-1), mx.reshape(-1)
@@ -138,7 +138,7 @@ class Observer(BaseObserver):
         for x2d in rows:
             for r in range(nrows):
                 ops.hist_update(x2d[r], rng[r], counts[r])
-        sbdist.sync_sum([counts])
+        yield sbdist.Sync.sum([counts], local=self._local)  # round 2: SUM
         hist = counts.to(torch.float32).cpu().numpy()  # torch.histc returns the input dtype
         bin_width = ((abs_max - (-abs_max)) / self.bins).cpu()
         idx = torch.tensor(

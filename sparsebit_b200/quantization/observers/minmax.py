@@ -10,8 +10,8 @@ class Observer(BaseObserver):
     TYPE = "minmax"
     KEEP_DATA = False
 
-    def calc_minmax(self):
-        min_val, max_val = self._running_minmax()
+    def calc_minmax_steps(self):
+        min_val, max_val = yield from self._running_minmax_steps()
         self._reset()
         self.min_val = min_val.to(self.device)
         self.max_val = max_val.to(self.device)

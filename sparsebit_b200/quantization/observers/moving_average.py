@@ -6,7 +6,6 @@ batch axis as the "channel" axis (4 B/elem, nothing cached).  The EMA itself is 
 recurrence over a few hundred scalars; it runs on the host with the reference's exact op order.
 With sharded calibration the per-sample extrema are all-gathered (rank-major sample order)."""
 import torch
-import torch.distributed as dist
 
 from ... import distributed as sbdist
 from ... import ops
@@ -36,14 +35,15 @@ class Observer(BaseObserver):
         ops.minmax_update(x.reshape(n, -1), st, 0)
         self._per_sample.append(torch.stack(ops.minmax_read(st)))  # [2, n]
 
-    def calc_minmax(self):
+    def _reset_state(self):
+        super()._reset_state()
+        self._per_sample = []
+
+    def calc_minmax_steps(self):
         assert self._per_sample, "No data cached!"
         stats = torch.cat(self._per_sample, dim=1)
-        if sbdist.active():
-            parts = [torch.empty_like(stats) for _ in range(dist.get_world_size())]
-            dist.all_gather(parts, stats)
-            stats = torch.cat(parts, dim=1)
-        mins, maxs = stats.cpu()
+        parts = yield sbdist.Sync.gather(stats)  # per-sample extrema of every rank, rank-major sample order
+        mins, maxs = torch.cat(parts, dim=1).cpu()
         r = self.ema_ratio
         min_val, max_val = mins[0], maxs[0]
         for i in range(1, mins.numel()):  # reference op order: r * acc + (1 - r) * sample, fp32

@@ -27,16 +27,16 @@ class Observer(BaseObserver):
         super().__init__(config, qdesc)
         self.alpha = config.OBSERVER.PERCENTILE.ALPHA  # read but unused by the reference too (Q8)
 
-    def calc_minmax(self, data_c_first=None):
-        min_val, max_val = self._running_minmax()
+    def calc_minmax_steps(self, data_c_first=None):
+        min_val, max_val = yield from self._running_minmax_steps()
         self.min_val = min_val.to(self.device)
         self.max_val = max_val.to(self.device)
         return self.min_val, self.max_val
 
-    def calc_qparams(self):
+    def calc_qparams_steps(self):
         rows = self.data_cache.rows(self.is_perchannel)
-        min_val, max_val = self.calc_minmax()
-        self.data_cache.reset()  # calc_qparams_with_minmax asserts an empty cache (Q10)
+        min_val, max_val = yield from self.calc_minmax_steps()  # round 1: MAX
+        self.data_cache.release()  # calc_qparams_with_minmax asserts an empty cache (Q10)
         dev = rows[0].device
         # python-double factors rounded once to fp32, exactly what `tensor * (1.0 - i * 0.01)` does
         factors = torch.tensor([1.0 - (i * 0.01) for i in range(STEPS)], dtype=torch.float64).to(torch.float32).to(dev)
@@ -53,7 +53,7 @@ class Observer(BaseObserver):
                 raise ops.SparsebitB200Error("mse observer: cached batches disagree on the channel count")
             ops.mse_sweep(x2d, cand_scale, cand_zp, qmin, qmax, sse)
             count += x2d.shape[1]
-        sbdist.sync_sum([sse, count])
+        yield sbdist.Sync.sum([sse, count], local=self._local)  # round 2: SUM
         loss = sse / count
         best = torch.argmin(loss, dim=1, keepdim=True)  # first minimal index == first strict improvement
         best_scale = torch.gather(cand_scale, 1, best).reshape(-1)

@@ -28,9 +28,9 @@ class Observer(BaseObserver):
     def _ingest(self, x):  # no running min/max needed
         pass
 
-    def calc_minmax(self):
+    def calc_minmax_steps(self):
         rows = self.data_cache.rows(self.is_perchannel)
-        self.data_cache.reset()
+        self.data_cache.release()
         dev = rows[0].device
         nrows = rows[0].shape[0]
         sel = ops.RadixSelect(nrows, 2, dev, key_mode=0)
@@ -38,13 +38,13 @@ class Observer(BaseObserver):
         for x2d in rows:
             sel.hist_pass(0, x2d, with_counts=True)
             total += x2d.shape[1]
-        sbdist.sync_sum([sel.hist, sel.counts, total])
+        yield sbdist.Sync.sum([sel.hist, sel.counts, total], local=self._local)
         sel.percentile_ranks(total, self.alpha)
         sel.scan(0)
         for p in (1, 2):
             for x2d in rows:
                 sel.hist_pass(p, x2d)
-            sbdist.sync_sum([sel.hist])
+            yield sbdist.Sync.sum([sel.hist], local=self._local)
             sel.scan(p)
         vals = sel.values().reshape(nrows, 2)
         counts = sel.counts.reshape(nrows, 2)

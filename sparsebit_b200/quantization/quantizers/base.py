@@ -8,6 +8,7 @@ import warnings
 import torch
 from torch import nn
 
+from ... import distributed as sbdist
 from ..observers import build_observer
 from ..quant_descriptor import QuantDescriptor
 from .quant_tensor import torch_fake_quant
@@ -49,10 +50,16 @@ class Quantizer(nn.Module, abc.ABC):
         self.zero_point = self._broadcast_qparams(zero_point)
         return self.scale, self.zero_point
 
-    def calc_qparams(self):
+    def calc_qparams_steps(self):
+        """``calc_qparams`` as a generator yielding the statistics to merge across ranks
+        (sparsebit_b200.distributed.Sync); the CalibrationRunner drives all quantizers of a model in lockstep."""
         if self.fake_fused:
             return self.scale, self.zero_point
-        return self._store_qparams(*self.observer.calc_qparams())
+        qparams = yield from self.observer.calc_qparams_steps()
+        return self._store_qparams(*qparams)
+
+    def calc_qparams(self):
+        return sbdist.drive(self.calc_qparams_steps())
 
     def calc_qparams_with_minmax(self, min_val, max_val):
         if self.fake_fused:

@@ -11,6 +11,7 @@ import warnings
 import torch
 import torch.nn as nn
 
+from ... import distributed as sbdist
 from ... import ops
 from . import Quantizer as BaseQuantizer
 from . import register_quantizer
@@ -54,21 +55,28 @@ class Quantizer(BaseQuantizer):
         self.init_params = False
         self.observer.keep_data = True  # the step-size initialisation needs the calibration batches themselves
 
-    def calc_qparams(self):
+    def calc_qparams_steps(self):
         if self.fake_fused or self.init_params:
             return self.scale, self.zero_point
         cache = self.observer.data_cache
-        # one native pass per cached batch: running min (negativity test) comes from the observer's streaming
-        # MinMax state, mean |x| from the fp64 row moments (sb200_observe_moments) -- no ATen reductions
-        running_min, _ = self.observer._running_minmax()
+        rows = cache.rows(self.is_perchannel)  # [C, M] per channel, [1, N] per tensor
+        # one native pass per cached batch: the running min (negativity test) comes from the streaming MinMax
+        # state (observers that keep none -- percentile, moving_average -- get one built from the cached rows),
+        # mean |x| from the fp64 row moments (sb200_observe_moments) -- no ATen reductions
+        obs = self.observer
+        if obs._mm_state is None:
+            obs._mm_state = ops.minmax_new(rows[0].shape[0], rows[0].device)
+            for r in rows:
+                ops.minmax_update(r, obs._mm_state, 0 if self.is_perchannel else None)
+        running_min, _ = yield from obs._running_minmax_steps()
         if bool((running_min < 0).any()) and not self.qdesc.is_symmetric:
             warnings.warn("Found data less than 0, reset quantizer scheme as symmetric")
             self.qdesc.set_symmetric(True)
-        rows = cache.rows(self.is_perchannel)  # [C, M] per channel, [1, N] per tensor
         acc = ops.moments_new(rows[0].shape[0], rows[0].device)
         for r in rows:
             ops.moments_update(r, acc)
-        count = sum(r.shape[1] for r in rows)
+        count = torch.tensor([float(sum(r.shape[1] for r in rows))], dtype=torch.float64, device=rows[0].device)
+        yield sbdist.Sync.sum([acc, count], local=obs._local)  # sharded calibration: moments of the WHOLE set
         total = acc[:, 2] if self.is_perchannel else acc[0, 2]
         scale = (2 * (total / count) / math.sqrt(self.qdesc.qmax)).to(torch.float32)
         self.observer._reset()

@@ -19,10 +19,10 @@ class Quantizer(BaseQuantizer):
         assert not self.qdesc.is_perchannel, "PACT no yet supports per-channel"
         self.init_alpha_value = config.QUANTIZER.PACT.ALPHA_VALUE
 
-    def calc_qparams(self):
+    def calc_qparams_steps(self):
         if self.fake_fused:
             return self.scale, self.zero_point
-        scale, zero_point = super().calc_qparams()
+        scale, zero_point = yield from super().calc_qparams_steps()
         self.alpha = nn.Parameter(torch.tensor([float(self.init_alpha_value)], device=self.device))
         return scale, zero_point
 

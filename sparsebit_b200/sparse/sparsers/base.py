@@ -12,7 +12,11 @@ class Sparser(nn.Module):
     def __init__(self, config, opr):
         super().__init__()
         sparser_cfg = config.SPARSER
-        self.config, self.opr = config, opr
+        self.config = config
+        # The owning operator registers this sparser as a submodule; registering the operator back as a submodule
+        # of the sparser would make the module tree cyclic (eval() / to() / state_dict() recurse forever).  The
+        # reference passes a repr string here (sparse/modules/base.py:23-24); keep the object, unregistered.
+        object.__setattr__(self, "opr", opr)
         self.type, self.strategy = sparser_cfg.TYPE, sparser_cfg.STRATEGY
         self.set_ratio(sparser_cfg.RATIO)
 

@@ -91,3 +91,94 @@ def test_pack_unpack_roundtrip_without_process_group():
     assert not sbdist.active()
     sbdist.sync_minmax(st)  # no-op when not enabled
     sbdist.sync_sum([torch.zeros(2)])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the lockstep driver: a whole "model" of observers (minmax-like, mse-like, percentile-like, moving-average-like,
+# one weight observer) merges with ONE collective per kind and round
+def _toy_observers(rank):
+    from sparsebit_b200.distributed import Sync
+
+    def minmax_like(seed):
+        rng = np.random.default_rng(seed + 1000 * rank)
+        st = _state(rng.standard_normal(3).astype(np.float32) - 1, rng.standard_normal(3).astype(np.float32) + 1)
+        yield Sync.max([st])
+        return _dec(st)
+
+    def mse_like(seed):
+        mm = yield from minmax_like(seed)
+        sse = torch.full((4,), float(rank + 1), dtype=torch.float64)
+        cnt = torch.tensor([10.0 * (rank + 1)], dtype=torch.float64)
+        yield Sync.sum([sse, cnt])
+        return mm, sse / cnt
+
+    def percentile_like():
+        hist = torch.arange(6, dtype=torch.int64) + rank
+        for _ in range(3):
+            yield Sync.sum([hist])
+        return hist
+
+    def moving_average_like():
+        parts = yield Sync.gather(torch.tensor([[float(rank)], [10.0 + rank]]))
+        return torch.cat(parts, dim=1)
+
+    def weight_like():
+        counts = torch.ones(5, dtype=torch.int64)
+        yield Sync.sum([counts], local=True)  # replicated weights: never summed across ranks
+        return counts
+
+    return [minmax_like(1), mse_like(2), percentile_like(), moving_average_like(), weight_like(), minmax_like(3)]
+
+
+def _worker_lockstep(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparsebit_b200 import distributed as sbdist
+
+    sbdist.enable()
+    sbdist.collectives(reset=True)
+    packed = sbdist.drive_all(_toy_observers(rank))
+    n_packed = sbdist.collectives(reset=True)
+    single = [sbdist.drive(g) for g in _toy_observers(rank)]
+    n_single = sbdist.collectives(reset=True)
+    if rank == 0:
+        torch.save({"packed": packed, "single": single, "n_packed": n_packed, "n_single": n_single}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lockstep_driver_packs_one_collective_per_round(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "lock.pt")
+    mp.spawn(_worker_lockstep, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    # round 1: MAX (3 states) + SUM (percentile pass 0) + gather; round 2: SUM (mse + percentile); round 3: SUM
+    assert got["n_packed"] == {"max": 1, "sum": 3, "gather": 1}
+    assert got["n_single"] == {"max": 3, "sum": 4, "gather": 1}
+
+    def same(a, b):
+        if isinstance(a, (tuple, list)):
+            return all(same(x, y) for x, y in zip(a, b))
+        return np.array_equal(np.asarray(a), np.asarray(b))
+
+    assert same(got["packed"], got["single"])
+    mm, loss = got["packed"][1]
+    assert torch.equal(loss, torch.full((4,), 3.0 / 30.0, dtype=torch.float64))
+    # three in-place SUM rounds over 2 ranks: (h0 + h1), then twice the sum of two identical copies
+    assert torch.equal(got["packed"][2], (torch.arange(6, dtype=torch.int64) * 2 + 1) * 4)
+    assert torch.equal(got["packed"][3], torch.tensor([[0.0, 1.0], [10.0, 11.0]]))             # rank-major gather
+    assert torch.equal(got["packed"][4], torch.ones(5, dtype=torch.int64))                     # weight stats stay local
+
+
+def test_drivers_without_process_group_are_passthrough():
+    from sparsebit_b200 import distributed as sbdist
+
+    assert not sbdist.active()
+    res = sbdist.drive_all(_toy_observers(0))
+    assert torch.equal(res[2], torch.arange(6, dtype=torch.int64))
+    assert torch.equal(res[3], torch.tensor([[0.0], [10.0]]))
+    assert sbdist.collectives() == {"max": 0, "sum": 0, "gather": 0}

@@ -102,6 +102,74 @@ def test_tcgen05_path_vs_fp64_oracle(bshape, k, n, gs):
             np.testing.assert_array_less(np.abs(yf[r] - ef[r]), 1e-5 + 1e-5 * mag)
 
 
+def _run_impl(x, qw, bias, scales, zeros, gs, impl, chunk_k=0):
+    from sparsebit_b200 import ops
+
+    y = t(np.broadcast_to(bias, x.shape[:-1] + (qw.shape[1],)).copy())
+    ops.gptq4_matmul(t(x), t(qw), y, t(scales), t(zeros), 0 if gs == -1 else gs, impl=impl, chunk_k=chunk_k)
+    return y.cpu().numpy()
+
+
+# tensor-memory-operand kernel (impl 3, gptq_ts.cu): ragged token / feature tiles, odd numbers of 64-K stages,
+# several chunks, group sizes 128 / 256 / 384, a single row, tiles of exactly 256 tokens and one more
+TS_CASES = [
+    ((1,), 128, 128, 128), ((128,), 256, 128, 128), ((130,), 512, 264, 128), ((29,), 8192, 1024, 128),
+    ((4,), 6144, 768, 384), ((300,), 1024, 512, 256), ((2, 130), 512, 260, 128), ((257,), 192 * 2, 132, 128),
+    ((256,), 4096, 4096, 128), ((64,), 11008, 512, 128), ((513,), 384, 392, -1), ((700,), 2048, 136, 128),
+]
+
+
+@pytest.mark.parametrize("bshape,k,n,gs", TS_CASES)
+def test_tcgen05_ts_path_vs_fp64_oracle(bshape, k, n, gs):
+    rng = np.random.default_rng(11 * k + n + len(bshape))
+    x, qw, bias, scales, zeros = _make_case(rng, bshape, k, n, gs)
+    y = _run_impl(x, qw, bias, scales, zeros, gs, impl=3)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, x.shape[:-1] + (n,)), scales, zeros, 0 if gs == -1 else gs)
+    np.testing.assert_allclose(y, exp, **TOL)  # the reference's elementwise form (test_cuda_kernel.py:47)
+
+
+def test_tcgen05_ts_outlier_rows_and_fp16_exact_activations():
+    rng = np.random.default_rng(3)
+    m, k, n = 300, 1024, 520
+    x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, 128)
+    x[0, :5] = [3e4, -7e4, 1e-6, 0.0, 123.0]  # fp16-overflowing magnitudes: per-row power-of-two scaling
+    x[2] *= 1e-4
+    y = _run_impl(x, qw, bias, scales, zeros, 128, impl=3)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (m, n)), scales, zeros, 128)
+    plain = [r for r in range(m) if r != 0]
+    np.testing.assert_allclose(y[plain], exp[plain], **TOL)
+    np.testing.assert_array_less(np.abs(y[0] - exp[0]), 1e-5 + 1e-5 * np.abs(exp[0]).max())
+    # fp16 activations cast to fp32 (the model path): the x_lo pass is skipped, rows are bit-identical to the
+    # three-pass result on the same data
+    xh = x.astype(np.float16).astype(np.float32)
+    xh[0, :2] = 1.0
+    y1 = _run_impl(xh, qw, bias, scales, zeros, 128, impl=3)
+    x2 = xh.copy()
+    x2[0, 0] += 1e-5
+    y2 = _run_impl(x2, qw, bias, scales, zeros, 128, impl=3)
+    np.testing.assert_allclose(y1, ogptq.dequant_matmul(xh, qw, np.broadcast_to(bias, (m, n)), scales, zeros, 128), **TOL)
+    np.testing.assert_allclose(y2[1:], y1[1:], rtol=0, atol=0)
+
+
+def test_tcgen05_ts_general_zero_points_and_chunking():
+    rng = np.random.default_rng(5)
+    x, qw, bias, scales, zeros = _make_case(rng, (200,), 1024, 384, 128)
+    exp_int = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (200, 384)), scales, zeros, 128)
+    for chunk in (64, 256, 512, 4096):  # accumulator drained every 1 / 4 / 8 stages, or once
+        np.testing.assert_allclose(_run_impl(x, qw, bias, scales, zeros, 128, impl=3, chunk_k=chunk), exp_int, **TOL)
+    # zeros that are NOT an integer multiple of scales: the prepare kernel clears the flag, the epilogue subtracts
+    # zeros * (row sums of x)
+    zeros2 = (zeros + 0.37 * scales * rng.uniform(0.5, 1.5, zeros.shape)).astype(np.float32)
+    zeros2[3, 2] = 0.0
+    y = _run_impl(x, qw, bias, scales, zeros2, 128, impl=3)
+    np.testing.assert_allclose(y, ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (200, 384)), scales, zeros2, 128), **TOL)
+    # integer zero points far outside [0, 15] (the contract allows any fp32 zeros)
+    zeros3 = (scales * np.rint(rng.uniform(-900, 900, zeros.shape))).astype(np.float32)
+    y = _run_impl(x, qw, bias, scales, zeros3, 128, impl=3)
+    exp3 = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (200, 384)), scales, zeros3, 128)
+    np.testing.assert_allclose(y, exp3, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(exp3).max()))
+
+
 @pytest.mark.parametrize("m,k,n", [(256, 1024, 512), (77, 512, 132)])
 def test_tcgen05_fp16_representable_activations_single_pass(m, k, n):
     """fp16 activations cast to fp32 (the reference's model path): lo == 0 everywhere, the kernel skips the
@@ -178,9 +246,11 @@ def test_linearity_and_accumulate_contract_at_llama_shape():
     np.testing.assert_allclose(y0, np.broadcast_to(bias, (m, n)), rtol=0, atol=1e-6)
     y2 = _run(2 * x, qw, np.zeros(n, np.float32), scales, zeros, 128)
     np.testing.assert_allclose(y2, 2 * (y1 - bias), rtol=2e-5, atol=2e-5)
-    rows = [0, 777, 2047]
-    exp = ogptq.dequant_matmul(x[rows], qw, np.broadcast_to(bias, (3, n)), scales, zeros, 128)
+    rows = [0, 255, 256, 777, 2047]
+    exp = ogptq.dequant_matmul(x[rows], qw, np.broadcast_to(bias, (len(rows), n)), scales, zeros, 128)
     np.testing.assert_allclose(y1[rows], exp, **TOL)
+    for impl in (2, 3):  # both tcgen05 kernels at the full shape
+        np.testing.assert_allclose(_run_impl(x, qw, bias, scales, zeros, 128, impl=impl)[rows], exp, **TOL)
 
 
 def test_argument_checks():

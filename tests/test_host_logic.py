@@ -146,7 +146,7 @@ class _StubQuantizer:
     def update_observer(self, x):
         self.seen.append(tuple(x.shape))
 
-    def calc_qparams(self):
+    def calc_qparams(self):  # a foreign quantizer without calc_qparams_steps: the runner calls this as one step
         self.calcs += 1
 
 
@@ -205,6 +205,44 @@ def test_calibration_runner_streaming_and_replay_feed_the_same_batches():
         assert net.a.weight_quantizer.seen == [(2, 2)]
         if asym or not streaming:
             assert net.a.flags == (False, False)  # quant switched back off after each replayed node
+
+
+def test_sparse_operator_with_a_built_sparser_is_not_a_cyclic_module():
+    """SparseOpr.build_sparser hands the operator to its sparser (sparse/modules/base.py:23-24 passes a repr
+    string): the sparser must not register it back as a submodule."""
+    from sparsebit_b200.sparse.modules import SConv2d, SLinear
+
+    for m in (SLinear(torch.nn.Linear(4, 3)), SConv2d(torch.nn.Conv2d(2, 3, 3))):
+        m.build_sparser(sbcfg.sparser_config(0.5))
+        assert m.sparser.opr is m
+        m.eval()
+        m.to("cpu")
+        assert set(m.state_dict()) >= {"weight", "w_mask"}
+        assert sum(1 for _ in m.modules()) == 2  # the operator and its sparser, nothing recursive
+
+
+def test_data_cache_reset_also_drops_the_owners_streaming_state():
+    """The reference idiom ``observer.data_cache.reset()`` (tools/calibration.py:113) must not leave a running
+    min/max, per-sample extrema or element counts behind (a replay would otherwise see every batch twice)."""
+    from sparsebit_b200.quantization.observers import build_observer
+    from sparsebit_b200.quantization.quant_descriptor import QuantDescriptor
+
+    cfg = sbcfg.quantizer_config("per-tensor-symmetric", 8, "feature", observer="aciq")
+    obs = build_observer(cfg, QuantDescriptor(cfg))
+    obs._mm_state, obs._numel = torch.zeros(2, dtype=torch.int32), 1234
+    obs.data_cache._batches, obs.data_cache._batch_size = 3, 12
+    obs.data_cache.reset()
+    assert obs._mm_state is None and obs._numel == 0 and len(obs.data_cache) == 0
+    cfg = sbcfg.quantizer_config("per-tensor-symmetric", 8, "feature", observer="moving_average")
+    obs = build_observer(cfg, QuantDescriptor(cfg))
+    obs._per_sample = [torch.zeros(2, 3)]
+    obs.data_cache.reset()
+    assert obs._per_sample == []
+    # release() only drops the retained batches
+    obs._mm_state = torch.zeros(2, dtype=torch.int32)
+    obs.data_cache._tensors, obs.data_cache._batches = [torch.zeros(1)], 1
+    obs.data_cache.release()
+    assert obs._mm_state is not None and len(obs.data_cache) == 0
 
 
 def test_quantlinear_pack_layouts_match_reference(golden):
