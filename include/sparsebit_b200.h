@@ -214,6 +214,11 @@ int sb200_observe_moments(const float* x, int64_t rows, int64_t row_len, const d
  * torch.bool storage).  thresh is a device float (from the radix select above with key_mode 1
  * and rank min(int(n*ratio), n-1), l1norm.py:19-21). */
 int sb200_mask_gt(const float* w, const float* thresh, uint8_t* mask, int64_t n, void* stream);
+/* Structured (filter) pruning, sparse/sparsers/l1norm.py:27-40: the per-filter L1 norms come from
+ * sb200_observe_moments (column 2 = sum |x|, fp64), the rank-th smallest from the radix select above, and
+ *   mask[r, :] = score[r] > thresh[0] ? 1.f : 0.f      (float mask shaped like the weight, as the reference builds). */
+int sb200_mask_rows_gt(const float* score, const float* thresh, float* mask, int64_t rows, int64_t inner,
+                       void* stream);
 /* out = w * mask    (sparse/modules/conv.py:40, linear.py:31).  mask: uint8 (bool). */
 int sb200_mask_apply(const float* w, const uint8_t* mask, float* out, int64_t n, void* stream);
 /* out = w * mask_f32   (mask stored as float ones_like when ratio == 0, l1norm.py:15-16). */
@@ -224,6 +229,25 @@ int sb200_mask_apply_qdq_perchannel(const float* w, const uint8_t* mask, const f
                                     const float* zero_point, float* out, int64_t outer,
                                     int64_t channels, int64_t inner, int qmin, int qmax,
                                     int rounding, void* stream);
+
+/* Multi-tensor form: the mask-apply + per-channel weight QDQ of EVERY QConv2d / QLinear of a model in one launch
+ * (modules/conv.py:37-42, linear.py:30-35 run them once per layer per forward; ResNet-50: 54 launch-bound kernels).
+ * Describe the tensors once -- sb200_qdq_multi_plan copies the table to `device_table`
+ * (sb200_qdq_multi_table_bytes(count) bytes, caller-owned) and returns the number of (tensor, row) work items --
+ * then every forward is one sb200_qdq_multi_run.  mask may be NULL per tensor; half-to-even rounding. */
+typedef struct sb200_qdq_tensor_desc {
+  const float* x;            /* device, [outer, channels, inner] contiguous */
+  const uint8_t* mask;       /* device uint8 (torch.bool), same shape as x, or NULL */
+  const float* scale;        /* device, `channels` floats */
+  const float* zero_point;   /* device, `channels` floats */
+  float* out;                /* device, same shape as x */
+  int64_t outer, channels, inner;
+  int qmin, qmax;
+} sb200_qdq_tensor_desc;
+size_t sb200_qdq_multi_table_bytes(int count);
+int sb200_qdq_multi_plan(const sb200_qdq_tensor_desc* descs, int count, void* device_table,
+                         size_t table_bytes, int64_t* total_rows, void* stream);
+int sb200_qdq_multi_run(const void* device_table, int count, int64_t total_rows, void* stream);
 
 /* ---- (3b) AdaRound weight quantizer (sparsebit/quantization/quantizers/adaround.py) -------
  * The one quantizer that bypasses STE.  [outer, channels, inner] geometry as above (per-tensor:
@@ -263,8 +287,9 @@ size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_si
 int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const float* scales,
                        const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                        int group_size, void* workspace, size_t workspace_bytes, void* stream);
-/* Per-call options instead of process-global switches.  impl: 0 = auto (M >= 128 -> 3, M >= 32 -> 2, else 1),
- * 1 = SIMT, 2 = tcgen05 with exact int4 operands and a per-128-K-group fp32 rescale of the accumulator,
+/* Per-call options instead of process-global switches.  impl: 0 = auto (M >= 768 -> 3, M >= 32 -> 2, else 1),
+ * 1 = small-M path (warp-level HMMA streaming kernel when N % 4 == 0, scalar kernel otherwise), 4 = scalar kernel,
+ * 2 = tcgen05 with exact int4 operands and a per-128-K-group fp32 rescale of the accumulator,
  * 3 = tcgen05 with the scaled weights as two fp16 planes written to tensor memory (A operand) and whole-K
  * accumulation, drained into fp32 registers every chunk_k K (multiple of 64; 0 = default 512) to bound the
  * tensor core's truncating accumulation. */
@@ -277,6 +302,18 @@ int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, co
                           const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                           int group_size, const sb200_gptq4_options* options, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* fp16 activations in, fp16 result out, WITHOUT the per-call casts of QuantLinear.forward (utils/quant.py:262-278 casts
+ * x / scales / zeros / bias to fp32, materialises y = bias, and casts the result back):
+ *   out_f16[m, n] = fp16( bias[n] + sum_k (scales * q - zeros) * x_f16[m, k] )          (overwrites out_f16)
+ * bias may be NULL; scales / zeros are the fp32 [N, G] tables.  Prefill-sized M runs the tensor-memory-operand
+ * tcgen05 kernel directly on the fp16 activations (their hi plane, no lo pass) and writes fp16 from the epilogue;
+ * smaller M is staged through fp32 inside the library.  Same accuracy as the fp32 entry point before the final
+ * rounding to fp16.  workspace: sb200_gptq4_linear_f16_workspace_bytes(...) bytes. */
+size_t sb200_gptq4_linear_f16_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size);
+int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_f16, const float* bias,
+                           const float* scales, const float* zeros, int64_t m, int64_t k, int64_t n,
+                           int64_t qweight_rows, int group_size, void* workspace, size_t workspace_bytes,
+                           void* stream);
 /* Any bit width of the reference's module: bits = 4 forwards to sb200_gptq4_matmul; bits = 3 / 2
  * replace vecquant3matmul / vecgroupquant3matmul / vecquant2matmul / vecgroupquant2matmul
  * (cuda_kernel.cpp:26-57,68-72; cuda_kernel_3bit.cu, cuda_kernel_2bit.cu).  Packed layouts of
@@ -287,7 +324,7 @@ int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const 
                       const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                       int bits, int group_size, void* workspace, size_t workspace_bytes, void* stream);
 /* Force a GPTQ implementation for sb200_gptq4_matmul (process-wide; tests / benchmarking only -- prefer the
- * per-call sb200_gptq4_matmul_ex): 0 = auto, 1 = SIMT, 2 / 3 = the two tcgen05 kernels. */
+ * per-call sb200_gptq4_matmul_ex): 0 = auto, 1 = small-M path, 2 / 3 = the two tcgen05 kernels, 4 = scalar kernel. */
 int sb200_gptq4_set_impl(int impl);
 
 /* Tuning knob of the tcgen05 kernel: nanoseconds its mostly-waiting roles (TMA producer, MMA issuer waiting for a

@@ -1,11 +1,15 @@
 """Turn ncu artefacts in gpurun_out/ into the small text summaries committed under profiles/.
-usage: python scripts/summarize_ncu.py <tag>"""
+usage: python scripts/summarize_ncu.py <tag> [report names ...]     (reports: gpurun_out/<name>_<tag>.ncu-rep)
+Also writes profiles/<tag>_traffic.json (DRAM bytes per algorithmic byte of the fused QDQ + stats kernel) when the
+report prof_qdq_stats_<tag> is present: bench.py's roofline.traffic reads it."""
 import collections
 import csv
+import json
 import subprocess
 import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+names = sys.argv[2:] or ["prof_qdq_stats", "prof_gptq_tc", "prof_gptq_simt", "prof_gptq_lowbit"]
 
 
 def launch_list():
@@ -75,9 +79,33 @@ try:
     open(f"profiles/{tag}_bench_launch_list.txt", "w").write(launch_list() + "\n")
 except Exception as e:
     print("launch list unchanged:", e)
-for name in ["prof_qdq_stats", "prof_gptq_tc", "prof_gptq_simt", "prof_gptq_lowbit"]:
+for name in names:
     try:
         open(f"profiles/{tag}_{name}.txt", "w").write(report(name) + "\n")
+        print("wrote", f"profiles/{tag}_{name}.txt")
     except Exception as e:
         print("skip", name, e)
-print(open(f"profiles/{tag}_bench_launch_list.txt").read())
+
+
+def traffic():
+    """dram__bytes_read + dram__bytes_write of the captured stream_kernel<TENSOR, STATS> launches over their
+    algorithmic bytes (8 B/elem; grid-stride kernel: elements = the bench's first activation sites)."""
+    raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_qdq_stats_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = sum(float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]] for r in rows[2:])
+    sites = [256 * 3 * 224 * 224, 256 * 64 * 56 * 56, 256 * 64 * 56 * 56][: len(rows) - 2]  # bench.py site order
+    ratio = total / (8.0 * sum(sites))
+    json.dump({"qdq_stats_pertensor": {"dram_bytes_per_algorithmic_byte": ratio, "launches": len(rows) - 2,
+                                       "note": f"dram__bytes_read.sum + dram__bytes_write.sum over {len(rows) - 2} captured launches "
+                                               f"(ncu --set full, {tag}) / 8 B per element"}},
+              open(f"profiles/{tag}_traffic.json", "w"), indent=1)
+    print("wrote", f"profiles/{tag}_traffic.json", ratio)
+
+
+try:
+    traffic()
+except Exception as e:
+    print("traffic summary skipped:", e)

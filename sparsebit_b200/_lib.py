@@ -58,15 +58,21 @@ PROTOTYPES = {
     "sb200_moments_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "sb200_observe_moments": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sb200_mask_gt": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "sb200_mask_rows_gt": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "sb200_mask_apply": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply_qdq_perchannel": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
+    "sb200_qdq_multi_table_bytes": (c_sz, [c_int]),
+    "sb200_qdq_multi_plan": (c_int, [c_vp, c_int, c_vp, c_sz, c_vp, c_vp]),
+    "sb200_qdq_multi_run": (c_int, [c_vp, c_int, c_i64, c_vp]),
     "sb200_adaround_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
     "sb200_adaround_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp]),
     "sb200_adaround_init": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "sb200_gptq4_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "sb200_gptq4_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_matmul_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "sb200_gptq4_linear_f16_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
+    "sb200_gptq4_linear_f16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_set_impl": (c_int, [c_int]),
     "sb200_gptq4_set_trace": (c_int, [c_vp]),

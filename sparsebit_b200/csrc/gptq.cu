@@ -3,11 +3,16 @@
 // Boundary replaced: cuda_kernel.vecquant4matmul / vecgroupquant4matmul
 // (large_language_models/llama/quantization/cuda/cuda_kernel.cpp:10-23,70,73) and their argument
 // checks (cuda_kernel_4bit.cu:44-60).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sb200 {
 int gptq4_simt(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
+bool gptq4_decode_supported(const int32_t* qweight, long long N);
+int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
+                 long long K, long long N, long long KW, int group_size, cudaStream_t st);
 bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
                         long long KW, int group_size);
 size_t gptq4_tc_workspace(long long M, long long K, long long N, int group_size);
@@ -17,12 +22,27 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
 size_t gptq4_ts_workspace(long long M, long long K, long long N, int group_size);
 int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
              long long K, long long N, long long KW, int group_size, int chunk_kb, void* workspace, size_t workspace_bytes,
-             cudaStream_t st);
+             cudaStream_t st, const __half* x_h = nullptr, __half* out_h = nullptr, const float* bias = nullptr);
 void gptq4_tc_set_trace(long long* p);
 void gptq4_tc_set_backoff(int ns);
 int gptq_lowbit(int bits, const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                 long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
 static int g_gptq_impl = 0;
+
+// fp16 <-> fp32 staging for the paths of sb200_gptq4_linear_f16 that run the fp32 kernels (small M)
+__global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
+}
+__global__ void __launch_bounds__(256) bias_rows_kernel(const float* __restrict__ bias, float* __restrict__ dst, long long rows, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * n; i += (long long)gridDim.x * blockDim.x) dst[i] = bias ? bias[i % n] : 0.f;
+}
+__global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __float2half_rn(src[i]);
+}
+static inline unsigned ew_grid(long long n) {
+  long long b = (n + 255) / 256, cap = (long long)sm_count() * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
 }  // namespace sb200
 
 using namespace sb200;
@@ -30,7 +50,7 @@ using namespace sb200;
 extern "C" {
 
 int sb200_gptq4_set_impl(int impl) {
-  SB_REQUIRE(impl >= 0 && impl <= 3, "sb200_gptq4_set_impl: impl must be 0, 1, 2 or 3 (got %d)", impl);
+  SB_REQUIRE(impl >= 0 && impl <= 4, "sb200_gptq4_set_impl: impl must be 0 .. 4 (got %d)", impl);
   g_gptq_impl = impl;
   return SB200_OK;
 }
@@ -63,7 +83,7 @@ static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, co
   SB_REQUIRE(qweight_rows >= (k + 7) / 8,
              "sb200_gptq4_matmul: qweight has %lld rows, need ceil(K/8) = %lld", (long long)qweight_rows,
              (long long)((k + 7) / 8));
-  SB_REQUIRE(impl >= 0 && impl <= 3, "sb200_gptq4_matmul: impl must be 0 (auto), 1 (SIMT), 2 or 3 (tcgen05) (got %d)", impl);
+  SB_REQUIRE(impl >= 0 && impl <= 4, "sb200_gptq4_matmul: impl must be 0 (auto), 1 (small-M), 2 or 3 (tcgen05), 4 (scalar) (got %d)", impl);
   SB_REQUIRE(chunk_k >= 0 && chunk_k % 64 == 0, "sb200_gptq4_matmul: chunk_k must be a multiple of 64 (got %d)", chunk_k);
   if (group_size != 0) {
     // cuda_kernel_4bit.cu:60
@@ -73,10 +93,11 @@ static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, co
     group_size = (int)k;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // 1 = SIMT (any shape);  2 = tcgen05, exact int4 operands + per-128-K-group fp32 rescale (gptq_tc.cu);
+  // 1 = small-M path: warp-level HMMA streaming kernel (gptq_decode.cu) when N % 4 == 0, else the scalar kernel;
+  // 4 = scalar SIMT kernel (gptq_simt.cu, any shape);  2 = tcgen05, exact int4 operands + per-128-K-group fp32 rescale (gptq_tc.cu);
   // 3 = tcgen05, scaled fp16 weight planes written to tensor memory, whole-K accumulation (gptq_ts.cu).
   int use = 1;
-  if (impl != 1) {
+  if (impl != 1 && impl != 4) {
     const bool shape_ok = gptq4_tc_supported(x, qweight, out, m, k, n, qweight_rows, group_size) && workspace;
     const bool ok2 = shape_ok && workspace_bytes >= gptq4_tc_workspace(m, k, n, group_size);
     const bool ok3 = shape_ok && workspace_bytes >= gptq4_ts_workspace(m, k, n, group_size);
@@ -87,7 +108,7 @@ static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, co
         return SB200_E_UNSUPPORTED;
       }
       use = impl;
-    } else if (ok3 && m >= 128) {
+    } else if (ok3 && m >= 768) {  // below that a 256-token tile leaves most SMs without a CTA (measured cross-over)
       use = 3;
     } else if (ok2 && m >= 32) {
       use = 2;
@@ -98,6 +119,8 @@ static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, co
                     workspace_bytes, st);
   if (use == 2)
     return gptq4_tc(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, workspace, workspace_bytes, st);
+  if (impl != 4 && gptq4_decode_supported(qweight, n))
+    return gptq4_decode(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
   return gptq4_simt(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
 }
 
@@ -114,6 +137,49 @@ int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, co
   const int impl = options ? options->impl : 0, chunk_k = options ? options->chunk_k : 0;
   return gptq4_dispatch(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, impl, chunk_k, workspace,
                         workspace_bytes, stream);
+}
+
+size_t sb200_gptq4_linear_f16_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size) {
+  if (m <= 0 || k <= 0 || n <= 0) return 0;
+  // fp32 staging of x and y for the small-M paths + the kernels' own workspace
+  return sb200_gptq4_workspace_bytes(m, k, n, group_size) + (size_t)m * (size_t)(k + n) * sizeof(float) + 2048;
+}
+
+int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_f16, const float* bias, const float* scales,
+                           const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(x_f16 && qweight && out_f16 && scales && zeros, "sb200_gptq4_linear_f16: null pointer argument");
+  SB_REQUIRE(m > 0 && k > 0 && n > 0, "sb200_gptq4_linear_f16: empty operand (M=%lld K=%lld N=%lld)", (long long)m, (long long)k, (long long)n);
+  SB_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && n < (1LL << 31), "sb200_gptq4_linear_f16: dimension too large");
+  SB_REQUIRE(qweight_rows >= (k + 7) / 8, "sb200_gptq4_linear_f16: qweight has %lld rows, need ceil(K/8) = %lld", (long long)qweight_rows, (long long)((k + 7) / 8));
+  if (group_size != 0) {
+    SB_REQUIRE(group_size > 0 && group_size % 128 == 0, "only group_size divisible by 128 is supported in 4-bit quantization (got %d)", group_size);
+  } else {
+    group_size = (int)k;
+  }
+  SB_REQUIRE(workspace && workspace_bytes >= sb200_gptq4_linear_f16_workspace_bytes(m, k, n, group_size), "sb200_gptq4_linear_f16: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const __half* xh = reinterpret_cast<const __half*>(x_f16);
+  __half* yh = reinterpret_cast<__half*>(out_f16);
+  const bool ts_ok = m >= 768 && (k % 8 == 0) && (n % 4 == 0) && aligned16(x_f16) && aligned16(qweight) &&
+                     gptq4_ts_workspace(m, k, n, group_size) > 0;
+  if (ts_ok)  // fp16 in, fp16 out, no fp32 round trip of x or y
+    return gptq4_ts(nullptr, qweight, nullptr, scales, zeros, m, k, n, qweight_rows, group_size, 0, workspace, workspace_bytes, st, xh, yh, bias);
+  // small M: stage through fp32 inside the library (a few MB at most) and run the fp32 kernels
+  unsigned char* ws = reinterpret_cast<unsigned char*>(((reinterpret_cast<uintptr_t>(workspace) + 255) / 256) * 256);
+  float* x32 = reinterpret_cast<float*>(ws);
+  float* y32 = x32 + (size_t)m * k;
+  unsigned char* rest = reinterpret_cast<unsigned char*>(y32 + (size_t)m * n);
+  const size_t rest_bytes = workspace_bytes - (size_t)(rest - reinterpret_cast<unsigned char*>(workspace));
+  f16_to_f32_kernel<<<ew_grid(m * k), 256, 0, st>>>(xh, x32, m * k);
+  SB_LAUNCHED();
+  bias_rows_kernel<<<ew_grid(m * n), 256, 0, st>>>(bias, y32, m, n);
+  SB_LAUNCHED();
+  const int rc = gptq4_dispatch(x32, qweight, y32, scales, zeros, m, k, n, qweight_rows, group_size, 0, 0, rest, rest_bytes, stream);
+  if (rc) return rc;
+  f32_to_f16_kernel<<<ew_grid(m * n), 256, 0, st>>>(y32, yh, m * n);
+  SB_LAUNCHED();
+  return SB200_OK;
 }
 
 int sb200_gptq_matmul(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,

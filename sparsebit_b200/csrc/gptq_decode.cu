@@ -1,0 +1,268 @@
+// gptq_decode.cu -- GPTQ int4 group-wise dequant-matmul for decode-sized M (1..32 tokens): HBM-bound, so the job is
+// to stream the packed weights once at full bandwidth with as few instructions per weight as possible.
+//
+// Replaces VecQuant4MatMulKernel (large_language_models/llama/quantization/cuda/cuda_kernel_4bit.cu:88-180) behind
+// the same contract:  out[m, n] += sum_k (scales[n, k/gs] * q[k, n] - zeros[n, k/gs]) * x[m, k].
+//
+// The scalar path (gptq_simt.cu) needs 3 instructions per weight (LOP3, FADD, FFMA) and is issue-bound at 0.27 of the
+// HBM roofline.  Here the multiply-accumulate goes to the tensor cores through the warp-level mma.sync.m16n8k16
+// (HMMA; tcgen05 needs 128-row tiles and TMEM, pointless for 1..32 tokens):
+//   A (16 features x 16 K)  = the int4 values as EXACT fp16 integers (q in [0, 15])
+//   B (16 K x 8 tokens)     = the activations x * 2^-e as fp16 hi (+ lo) planes, staged once per CTA in shared memory
+//   D (16 x 8 fp32)         = integer dot products of one 128-K group; the group's scale / zero are applied in fp32:
+//                             acc += scale * D - zeros * sum_k x        (same factoring as the scalar path)
+// which costs ~1.3 instructions per weight: per 32-K chunk a lane issues one LDG.128 (4 packed words = 4 feature
+// rows x 8 K), 9 ALU instructions per word to expand it into A fragments, one LDS.128 for the B fragments of both
+// K halves and 4 HMMAs (8 with the lo plane; skipped when the activations are fp16-exact, the model path).
+//
+// Fragment bookkeeping.  K order inside a tile is free as long as A and B agree, and so is the row order.  Lane
+// (g = lane / 4, c = lane % 4) loads the packed row kw = 4 * chunk + c for the four features n = nbase + 4 g + {0..3}
+// (a warp covers 32 features x 4 packed rows: four full 128-byte lines per load instruction), which become
+//   tile T in {0, 1}: row slot g  <-> feature 4 g + 2 T,   row slot g + 8 <-> feature 4 g + 2 T + 1
+// and each word feeds two MMAs i in {0, 1}: columns (2c, 2c+1) <-> nibbles (2i, 2i + 4), columns (2c + 8, 2c + 9) <->
+// nibbles (2i + 1, 2i + 5) -- exactly the pairs one LOP3 extracts ((w >> 8i) & 0x000F000F, & 0x00F000F0).  The
+// activations are stored in shared memory with every 8 K permuted to (0, 4, 1, 5, 2, 6, 3, 7), so one 16-byte load
+// returns the B registers of both MMAs.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace sb200 {
+
+constexpr int kDecThreads = 128;  // 4 warps x 32 features
+constexpr int kDecCols = 128;
+constexpr int kDecBlockK = 128;
+
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t dec_and_or(uint32_t x, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "n"(MASK), "r"(c));
+  return r;
+}
+__device__ __forceinline__ void hmma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// NB = number of 8-token blocks (tokens handled per pass = 8 * NB).  Dynamic shared memory:
+//   xh[8 NB][stride], xl[8 NB][stride] halves (stride = slice_k + 32: token rows start 64 bytes apart modulo 128, so the
+//   8 lanes of an LDS.128 phase hit distinct banks), xsum[8 NB][blocks_per_slice] floats, escale[8 NB] floats.
+template <int NB>
+__global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* __restrict__ x, const uint32_t* __restrict__ qw,
+                                                                 float* __restrict__ out, const float* __restrict__ scales,
+                                                                 const float* __restrict__ zeros, int M, int K, int N, int KW,
+                                                                 int G, int group_size, int blocks_per_slice) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  constexpr int MT = 8 * NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const int nblk = (K + kDecBlockK - 1) / kDecBlockK;
+  const int b0 = blockIdx.y * blocks_per_slice;
+  const int nb = min(b0 + blocks_per_slice, nblk) - b0;
+  const int slice_k = blocks_per_slice * kDecBlockK;
+  const int stride = slice_k + 32;  // halves
+  __half* xh = reinterpret_cast<__half*>(dsm);
+  __half* xl = xh + MT * stride;
+  float* xsum = reinterpret_cast<float*>(xl + MT * stride);
+  float* escale = xsum + MT * blocks_per_slice;
+  __shared__ int s_need_lo;
+  __shared__ unsigned int s_amax[32];
+  const int nbase = blockIdx.x * kDecCols + warp * 32 + 4 * g;  // this lane's four features nbase .. nbase + 3
+  const bool col_ok = nbase < N;                                  // N % 4 == 0: all four or none
+  uint32_t bias;
+  asm volatile("mov.b32 %0, 0x64006400;" : "=r"(bias));  // half2(1024, 1024), opaque to constant propagation
+  const __half2 k1024 = __float2half2_rn(1024.f), k16 = __float2half2_rn(0.0625f), k64n = __float2half2_rn(-64.f);
+
+  auto load_group = [&](int bl, uint4 (&w)[4]) {  // the four 32-K chunks of one 128-K block
+    const int row0 = (b0 + bl) * (kDecBlockK / 8) + c;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int row = row0 + 4 * ch;
+      w[ch] = (col_ok && row < KW) ? __ldcs(reinterpret_cast<const uint4*>(qw + (size_t)row * N + nbase)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+
+  for (int m0 = 0; m0 < M; m0 += MT) {
+    // The kernel lives for a few microseconds, i.e. a handful of DRAM latencies: the packed weights of the first two
+    // 128-K blocks are requested before anything else, so their latency overlaps the staging of the activations.
+    uint4 wa[4], wb[4];
+    load_group(0, wa);
+    if (nb > 1) load_group(1, wb);
+    __syncthreads();  // the previous pass is done with the staging buffers
+    const int tokens = min(MT, M - m0);  // real tokens of this pass; the other token columns of the MMA are never read back
+    if (tid < MT) s_amax[tid] = 0u;
+    if (tid == 0) s_need_lo = 0;
+    __syncthreads();
+    // ---- stage the activations of this K slice (work items = (token, 128-K block) pairs spread over the warps):
+    // per-token power-of-two scale, fp16 hi / lo planes, 8-K permutation, per-block row sums
+    const int pairs = tokens * blocks_per_slice;
+    for (int p = warp; p < pairs; p += kDecThreads / 32) {
+      const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
+      const float* xr = x + (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
+      float amax = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int kk = r * 32 + lane;
+        if (blk < nb && (b0 + blk) * kDecBlockK + kk < K) amax = fmaxf(amax, fabsf(__ldg(xr + kk)));
+      }
+      amax = warp_max(amax);
+      if (lane == 0 && amax < __int_as_float(0x7f800000)) atomicMax(&s_amax[t], __float_as_uint(amax));  // non-negative: bit order == value order
+    }
+    __syncthreads();
+    for (int p = warp; p < pairs; p += kDecThreads / 32) {
+      const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
+      const float* xr = x + (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
+      const float amax = __uint_as_float(s_amax[t]);
+      const int e = amax > 0.f ? ilogbf(amax) - 14 : 0;  // scaled slice max in [2^14, 2^15)
+      const float down = ldexpf(1.f, -e);
+      if (lane == 0 && blk == 0) escale[t] = ldexpf(1.f, e);
+      float s = 0.f;
+      bool any_lo = false;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int kk = r * 32 + lane;
+        const bool ok = blk < nb && ((b0 + blk) * kDecBlockK + kk < K);
+        const float v = ok ? __ldg(xr + kk) * down : 0.f;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        any_lo |= (__half_as_ushort(lo) & 0x7FFFu) != 0;
+        const int j = kk & 7, pos = blk * kDecBlockK + (kk & ~7) + ((j & 3) << 1) + (j >> 2);  // (0,4,1,5,2,6,3,7)
+        xh[t * stride + pos] = hi;
+        xl[t * stride + pos] = lo;
+        s += v;
+      }
+      s = warp_sum(s);
+      if (lane == 0) xsum[t * blocks_per_slice + blk] = s;
+      if (__any_sync(0xffffffffu, any_lo) && lane == 0) atomicOr(&s_need_lo, 1);
+    }
+    __syncthreads();
+    const bool need_lo = s_need_lo != 0;
+
+    float acc[2][NB][4];
+#pragma unroll
+    for (int T = 0; T < 2; ++T)
+#pragma unroll
+      for (int q = 0; q < NB; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[T][q][j] = 0.f;
+
+    auto compute_group = [&](int bl, const uint4 (&w)[4]) {
+      float d[2][NB][4];
+#pragma unroll
+      for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[T][q][j] = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        // B fragments of this chunk: tokens g (+ 8 q), K = 32 (bl*4 + ch) + 8 c .. + 7 in permuted order
+        uint4 bh[NB], bl4[NB];
+        const int koff = (bl * 4 + ch) * 32 + 8 * c;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          bh[q] = *reinterpret_cast<const uint4*>(xh + (q * 8 + g) * stride + koff);
+          if (need_lo) bl4[q] = *reinterpret_cast<const uint4*>(xl + (q * 8 + g) * stride + koff);
+        }
+        const uint32_t words[4] = {w[ch].x, w[ch].y, w[ch].z, w[ch].w};  // features nbase + 0..3
+#pragma unroll
+        for (int T = 0; T < 2; ++T) {
+          uint32_t a0[4], a1[4];  // A fragments of MMA i = 0 and i = 1
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // row slot g (h = 0) / g + 8 (h = 1)
+            const uint32_t wlo = words[2 * T + h], whi = wlo >> 8;
+            const uint32_t u0 = dec_and_or<0x000F000Fu>(wlo, bias), u1 = dec_and_or<0x00F000F0u>(wlo, bias);
+            const uint32_t u2 = dec_and_or<0x000F000Fu>(whi, bias), u3 = dec_and_or<0x00F000F0u>(whi, bias);
+            const __half2 q0 = __hsub2(*reinterpret_cast<const __half2*>(&u0), k1024);        // nibbles (0, 4)
+            const __half2 q1 = __hfma2(*reinterpret_cast<const __half2*>(&u1), k16, k64n);    // nibbles (1, 5)
+            const __half2 q2 = __hsub2(*reinterpret_cast<const __half2*>(&u2), k1024);        // nibbles (2, 6)
+            const __half2 q3 = __hfma2(*reinterpret_cast<const __half2*>(&u3), k16, k64n);    // nibbles (3, 7)
+            a0[h] = *reinterpret_cast<const uint32_t*>(&q0);      // columns (2c, 2c + 1)
+            a0[2 + h] = *reinterpret_cast<const uint32_t*>(&q1);  // columns (2c + 8, 2c + 9)
+            a1[h] = *reinterpret_cast<const uint32_t*>(&q2);
+            a1[2 + h] = *reinterpret_cast<const uint32_t*>(&q3);
+          }
+#pragma unroll
+          for (int q = 0; q < NB; ++q) {
+            hmma_16816(d[T][q], a0, bh[q].x, bh[q].y);
+            hmma_16816(d[T][q], a1, bh[q].z, bh[q].w);
+            if (need_lo) {
+              hmma_16816(d[T][q], a0, bl4[q].x, bl4[q].y);
+              hmma_16816(d[T][q], a1, bl4[q].z, bl4[q].w);
+            }
+          }
+        }
+      }
+      // group epilogue: acc += scale * D - zeros * sum_k x   (rows: slot g -> feature 2T, slot g + 8 -> feature 2T + 1)
+      const int grp = ((b0 + bl) * kDecBlockK) / group_size;
+#pragma unroll
+      for (int T = 0; T < 2; ++T) {
+        const int nA = nbase + 2 * T;
+        const float sA = col_ok ? __ldg(scales + (size_t)nA * G + grp) : 0.f, zA = col_ok ? __ldg(zeros + (size_t)nA * G + grp) : 0.f;
+        const float sB = col_ok ? __ldg(scales + (size_t)(nA + 1) * G + grp) : 0.f, zB = col_ok ? __ldg(zeros + (size_t)(nA + 1) * G + grp) : 0.f;
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const float xs0 = xsum[(q * 8 + 2 * c) * blocks_per_slice + bl], xs1 = xsum[(q * 8 + 2 * c + 1) * blocks_per_slice + bl];
+          acc[T][q][0] += fmaf(sA, d[T][q][0], -zA * xs0);
+          acc[T][q][1] += fmaf(sA, d[T][q][1], -zA * xs1);
+          acc[T][q][2] += fmaf(sB, d[T][q][2], -zB * xs0);
+          acc[T][q][3] += fmaf(sB, d[T][q][3], -zB * xs1);
+        }
+      }
+    };
+    for (int bl = 0; bl < nb; bl += 2) {
+      compute_group(bl, wa);
+      if (bl + 2 < nb) load_group(bl + 2, wa);
+      if (bl + 1 < nb) {
+        compute_group(bl + 1, wb);
+        if (bl + 3 < nb) load_group(bl + 3, wb);
+      }
+    }
+    if (col_ok) {
+#pragma unroll
+      for (int T = 0; T < 2; ++T)
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int tok = q * 8 + 2 * c + (j & 1), m = m0 + tok;
+            const int n = nbase + 2 * T + (j >> 1);
+            if (m < M) atomicAdd(out + (size_t)m * N + n, acc[T][q][j] * escale[tok]);
+          }
+    }
+  }
+}
+
+bool gptq4_decode_supported(const int32_t* qweight, long long N) { return (N % 4 == 0) && aligned16(qweight); }
+
+int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
+                 long long K, long long N, long long KW, int group_size, cudaStream_t st) {
+  const int G = (int)((K + group_size - 1) / group_size);
+  const int nblk = (int)((K + kDecBlockK - 1) / kDecBlockK);
+  const int colblocks = (int)((N + kDecCols - 1) / kDecCols);
+  const int nbk = M <= 8 ? 1 : (M <= 16 ? 2 : 4);
+  // K slices: ~5 CTAs per SM (what the register file holds: 4 warps x 96 registers), each streaming as long a K
+  // range as that allows, bounded by the activation slice held in shared memory
+  int want = (sm_count() * 5 + colblocks - 1) / colblocks;
+  if (want < 1) want = 1;
+  if (want > nblk) want = nblk;
+  int S = (nblk + want - 1) / want;
+  const int smax = nbk == 1 ? 8 : (nbk == 2 ? 4 : 2);
+  if (S > smax) S = smax;
+  const int slices = (nblk + S - 1) / S;
+  const dim3 grid((unsigned)colblocks, (unsigned)slices);
+  const uint32_t* qw = reinterpret_cast<const uint32_t*>(qweight);
+  const int mt = 8 * nbk;
+  const size_t smem = (size_t)2 * mt * (S * kDecBlockK + 32) * sizeof(__half) + (size_t)mt * S * sizeof(float) + (size_t)mt * sizeof(float);
+#define SB_GO(NB_) \
+  gptq4_decode_kernel<NB_><<<grid, kDecThreads, smem, st>>>(x, qw, out, scales, zeros, (int)M, (int)K, (int)N, (int)KW, G, group_size, S)
+  if (nbk == 1) SB_GO(1);
+  else if (nbk == 2) SB_GO(2);
+  else SB_GO(4);
+#undef SB_GO
+  SB_LAUNCHED();
+  return SB200_OK;
+}
+
+}  // namespace sb200

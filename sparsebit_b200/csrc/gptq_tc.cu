@@ -218,6 +218,12 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         if (need_lo) tma_load_2d(st + kABytes, &map_lo, kb * kBlockK, m0, &sm->full[s]);
         tma_load_2d(st + 2 * kABytes + kBBytes, &map_q, n0, kb * (kBlockK / 8), &sm->full[s]);
       }
+      // drain the asynchronous tcgen05.commit arrivals on empty[] of the last stages before the CTA may exit
+      for (int kb = num_kb; kb < num_kb + kStages; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        mbar_wait_relaxed(&sm->empty[s], ph ^ 1u, backoff_ns);
+      }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
@@ -449,25 +455,15 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const float rs = __ldg(rowscale + m);
       float* orow = out + (size_t)m * N + n0 + col0;
       if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
-        // four independent 128-bit loads in flight, then four stores (a load-modify-store per float4 would be
-        // 16 serialised global round trips: the compiler cannot reorder a load above the previous store)
 #pragma unroll
-        for (int b4 = 0; b4 < 16; b4 += 4) {
-          float4 o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o[i] = (n0 + col0 + 4 * (b4 + i) < N) ? __ldcg(reinterpret_cast<const float4*>(orow + 4 * (b4 + i)))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j4 = b4 + i;
-            if (n0 + col0 + 4 * j4 < N) {
-              o[i].x = fmaf(rs, acc[4 * j4 + 0], o[i].x);
-              o[i].y = fmaf(rs, acc[4 * j4 + 1], o[i].y);
-              o[i].z = fmaf(rs, acc[4 * j4 + 2], o[i].z);
-              o[i].w = fmaf(rs, acc[4 * j4 + 3], o[i].w);
-              __stcg(reinterpret_cast<float4*>(orow + 4 * j4), o[i]);
-            }
+        for (int j4 = 0; j4 < 16; ++j4) {
+          if (n0 + col0 + 4 * j4 < N) {
+            float4 o = *reinterpret_cast<float4*>(orow + 4 * j4);
+            o.x = fmaf(rs, acc[4 * j4 + 0], o.x);
+            o.y = fmaf(rs, acc[4 * j4 + 1], o.y);
+            o.z = fmaf(rs, acc[4 * j4 + 2], o.z);
+            o.w = fmaf(rs, acc[4 * j4 + 3], o.w);
+            *reinterpret_cast<float4*>(orow + 4 * j4) = o;
           }
         }
       } else {

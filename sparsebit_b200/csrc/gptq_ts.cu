@@ -24,7 +24,7 @@
 // that add with round-to-nearest; the drain moves 128 KB out of TMEM with tcgen05.ld.x8 (256 B/clk) while the
 // producers keep running ahead through the 3-stage ring.
 //
-// Roles (640 threads, 1 CTA / SM; the CTA owns a 128-feature x 256-token output tile over all of K):
+// Roles (640 threads, one persistent CTA per SM; a tile = 128 features x 256 tokens over all of K):
 //   warp 0      TMA producer: x_hi (+ x_lo) tile and the packed 8 x 128 int32 weight tile per stage
 //   warp 1      MMA issuer (elect.sync lane), tcgen05.commit -> stage empty / chunk complete
 //   warp 2      TMEM allocator (512 columns: 256 accumulator + 3 stages x (32 hi + 32 lo) operand columns)
@@ -111,24 +111,29 @@ __device__ __forceinline__ __half2 u2h2(uint32_t v) { return *reinterpret_cast<c
 __device__ __forceinline__ uint32_t h22u(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
 // ---------------------------------------------------------------------------------- main kernel
+// Persistent: one CTA per SM walks the output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (token tile fastest,
+// so CTAs running side by side share the packed weight tile through L2).  Stage and accumulator phases run on
+// counters that continue across tiles, so the producers start the next tile while the epilogue still writes the
+// previous one to global memory.
 __global__ void __launch_bounds__(kTsThreads, 1)
 gptq4_ts_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                 const __grid_constant__ CUtensorMap map_q, float* __restrict__ out, const float* __restrict__ scales,
                 const float* __restrict__ zeros,
                 const float* __restrict__ xsum, const float* __restrict__ rowscale, const uint2* __restrict__ sz,
                 const float* __restrict__ colscale, const int* __restrict__ flags, int M, int K, int N, int Gq, int G128,
-                int group_size, int chunk_kb) {
+                int group_size, int chunk_kb, __half* __restrict__ out_h, const float* __restrict__ bias) {
+  // out_h != nullptr: fp16 result  out_h[m, n] = bias[n] + x @ W  (overwrite, no read of `out`); otherwise the fp32
+  // accumulate-in-place contract of the reference kernel, out[m, n] += x @ W.
   extern __shared__ unsigned char smem_raw[];
   unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   TsSmem* sm = reinterpret_cast<TsSmem*>(stage_base + (size_t)kTsStages * kTsStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTok, n0 = blockIdx.y * kWRows;
   const int num_kb = (K + kTsBK - 1) / kTsBK;
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+  const int tiles_m = (M + kTok - 1) / kTok;
+  const int num_tiles = tiles_m * ((N + kWRows - 1) / kWRows);
   const bool int_zero = flags[0] != 0;  // uniform: every zeros[n, g] is an integer multiple of scales[n, g] (no residual)
   const bool need_lo = flags[1] != 0;   // uniform: some activation has a non-zero fp16 low part
-  // tokens this tile really has, rounded up to the MMA's N granularity (TMA zero-fills the rows beyond M)
-  const int tok_n = min(kTok, ((M - m0 + 15) >> 4) << 4);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
@@ -161,123 +166,142 @@ gptq4_ts_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     // ================================================================== TMA producer
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(kXBytes + kQBytes + (need_lo ? kXBytes : 0));
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kTsStages;
-        const uint32_t ph = (uint32_t)(kb / kTsStages) & 1u;
+      uint32_t it = 0;  // stage counter, continues across tiles
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * kTok, n0 = (tile / tiles_m) * kWRows;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % kTsStages, ph = (it / kTsStages) & 1u;
+          mbar_wait_relaxed(&sm->empty[s], ph ^ 1u, 0);
+          unsigned char* st = stage_base + (size_t)s * kTsStageBytes;
+          mbar_expect_tx(&sm->full[s], tx);
+          tma_load_2d(st, &map_hi, kb * kTsBK, m0, &sm->full[s]);
+          if (need_lo) tma_load_2d(st + kXBytes, &map_lo, kb * kTsBK, m0, &sm->full[s]);
+          tma_load_2d(st + 2 * kXBytes, &map_q, n0, kb * (kTsBK / 8), &sm->full[s]);
+        }
+      }
+      // Drain: the tcgen05.commit arrivals on empty[] of the last stages are asynchronous and nobody else waits for
+      // them.  The CTA must not exit while one is in flight (with a handful of tokens the epilogue finishes within
+      // nanoseconds of the last MMA): wait for each stage exactly as if one more load were to be issued into it.
+      for (int d = 0; d < kTsStages; ++d, ++it) {
+        const uint32_t s = it % kTsStages, ph = (it / kTsStages) & 1u;
         mbar_wait_relaxed(&sm->empty[s], ph ^ 1u, 0);
-        unsigned char* st = stage_base + (size_t)s * kTsStageBytes;
-        mbar_expect_tx(&sm->full[s], tx);
-        tma_load_2d(st, &map_hi, kb * kTsBK, m0, &sm->full[s]);
-        if (need_lo) tma_load_2d(st + kXBytes, &map_lo, kb * kTsBK, m0, &sm->full[s]);
-        tma_load_2d(st + 2 * kXBytes, &map_q, n0, kb * (kTsBK / 8), &sm->full[s]);
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
     const uint32_t stage0 = smem_u32(stage_base);
     const uint64_t dconst = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    // instruction descriptor: D = F32, A = B = F16, K-major, N = tok_n, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(tok_n >> 3) << 17) | ((uint32_t)(kWRows >> 4) << 24);
-    int kb = 0;
-    for (int c = 0; c < num_chunks; ++c) {
-      if (c > 0) mbar_wait(&sm->acc_empty, (uint32_t)(c - 1) & 1u);  // the previous chunk left the accumulator
-      const int kb_end = min(num_kb, kb + chunk_kb);
-      for (bool first = true; kb < kb_end; ++kb, first = false) {
-        const int s = kb % kTsStages;
-        const uint32_t ph = (uint32_t)(kb / kTsStages) & 1u;
-        mbar_wait(&sm->ready[s], ph);  // implies full[s]: the unpack warps waited for it
-        tc_fence_after();
-        const uint32_t xh = stage0 + (uint32_t)s * kTsStageBytes;
-        const uint64_t dbh = dconst | (uint64_t)((xh >> 4) & 0x3FFFu);
-        const uint64_t dbl = dconst | (uint64_t)(((xh + kXBytes) >> 4) & 0x3FFFu);
-        const uint32_t a_hi = tmem_base + kAccCols + (uint32_t)s * kAStageCols;
-        const uint32_t a_lo = a_hi + 32;
-        if (elect_one()) {
+    uint32_t it = 0, cc = 0;  // stage / chunk counters, continue across tiles
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * kTok;
+      // tokens this tile really has, rounded up to the MMA's N granularity (TMA zero-fills the rows beyond M)
+      const int tok_n = min(kTok, ((M - m0 + 15) >> 4) << 4);
+      // instruction descriptor: D = F32, A = B = F16, K-major, N = tok_n, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(tok_n >> 3) << 17) | ((uint32_t)(kWRows >> 4) << 24);
+      int kb = 0;
+      for (int c = 0; c < num_chunks; ++c, ++cc) {
+        if (cc > 0) mbar_wait(&sm->acc_empty, (cc - 1) & 1u);  // the previous chunk left the accumulator
+        const int kb_end = min(num_kb, kb + chunk_kb);
+        for (bool first = true; kb < kb_end; ++kb, ++it, first = false) {
+          const uint32_t s = it % kTsStages, ph = (it / kTsStages) & 1u;
+          mbar_wait(&sm->ready[s], ph);  // implies full[s]: the unpack warps waited for it
+          tc_fence_after();
+          const uint32_t xh = stage0 + s * kTsStageBytes;
+          const uint64_t dbh = dconst | (uint64_t)((xh >> 4) & 0x3FFFu);
+          const uint64_t dbl = dconst | (uint64_t)(((xh + kXBytes) >> 4) & 0x3FFFu);
+          const uint32_t a_hi = tmem_base + kAccCols + s * kAStageCols;
+          const uint32_t a_lo = a_hi + 32;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kTsBK / 16; ++k)  // 16 K = 8 TMEM columns of A, 32 bytes of B
-            tc_mma_f16_ts(tmem_base, a_hi + 8 * k, dbh + 2 * k, idesc, !(first && k == 0));
+            for (int k = 0; k < kTsBK / 16; ++k)  // 16 K = 8 TMEM columns of A, 32 bytes of B
+              tc_mma_f16_ts(tmem_base, a_hi + 8 * k, dbh + 2 * k, idesc, !(first && k == 0));
 #pragma unroll
-          for (int k = 0; k < kTsBK / 16; ++k) tc_mma_f16_ts(tmem_base, a_lo + 8 * k, dbh + 2 * k, idesc, true);
-          if (need_lo) {
+            for (int k = 0; k < kTsBK / 16; ++k) tc_mma_f16_ts(tmem_base, a_lo + 8 * k, dbh + 2 * k, idesc, true);
+            if (need_lo) {
 #pragma unroll
-            for (int k = 0; k < kTsBK / 16; ++k) tc_mma_f16_ts(tmem_base, a_hi + 8 * k, dbl + 2 * k, idesc, true);
+              for (int k = 0; k < kTsBK / 16; ++k) tc_mma_f16_ts(tmem_base, a_hi + 8 * k, dbl + 2 * k, idesc, true);
+            }
+            tc_commit(&sm->empty[s]);
+            if (kb == kb_end - 1) tc_commit(&sm->acc_full);
           }
-          tc_commit(&sm->empty[s]);
-          if (kb == kb_end - 1) tc_commit(&sm->acc_full);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp >= 12) {
     // ================================================================== unpack: packed int4 -> scaled fp16 planes in TMEM
     reg_dec<56>();
     const int t = (threadIdx.x - 12 * 32) & 127;  // feature row of the tile = TMEM lane
-    const int uset = (warp - 12) >> 2;
-    const int n = n0 + t;
-    const bool live = n < N;
+    const uint32_t uset = (uint32_t)(warp - 12) >> 2;
     uint32_t bias;
     asm volatile("mov.b32 %0, 0x64006400;" : "=r"(bias));  // half2(1024, 1024); opaque to constant propagation
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCols;
     const __half2 k16 = __float2half2_rn(0.0625f);
-    // quantisation group of the stage, advanced incrementally; its parameters are fetched one iteration ahead
-    int gq_next = (uset * kTsBK) / group_size;
-    long long koff_next = (long long)uset * kTsBK;
-    auto fetch = [&](int kb) -> uint2 {
-      if (!live || kb >= num_kb) return make_uint2(0u, 0u);
-      return __ldg(sz + (size_t)n * Gq + gq_next);
-    };
-    uint2 p_cur = fetch(uset);
-    for (int kb = uset; kb < num_kb; kb += 2) {
-      const int s = kb % kTsStages;
-      const uint32_t ph = (uint32_t)(kb / kTsStages) & 1u;
-      koff_next += 2 * kTsBK;
-      while (koff_next >= (long long)(gq_next + 1) * group_size) ++gq_next;
-      const uint2 p_next = fetch(kb + 2);
-      // scale planes and zero point of this stage's group
-      const __half2 sh2 = __half2half2(__ushort_as_half((unsigned short)(p_cur.x & 0xFFFFu)));
-      const __half2 sl2 = __half2half2(__ushort_as_half((unsigned short)(p_cur.x >> 16)));
-      const float zf = __half2float(__ushort_as_half((unsigned short)p_cur.y));
-      const __half2 zsub = __float2half2_rn(1024.f + zf);  // exact: |zero| <= 1024
-      const __half2 noff = __float2half2_rn(-(64.f + zf));
-      p_cur = p_next;
-      mbar_wait_relaxed(&sm->full[s], ph, 0);
-      const uint32_t* bq = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * kTsStageBytes + 2 * kXBytes);
-      uint32_t w[kTsBK / 8];
+    uint32_t it0 = 0;  // stage counter of the tile's first K block; this set takes the stages with (it % 2) == uset
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it0 += (uint32_t)num_kb) {
+      const int n = (tile / tiles_m) * kWRows + t;
+      const bool live = n < N;
+      const int kb0 = (int)((it0 + uset) & 1u);  // first K block of this tile that belongs to this set
+      // quantisation group of the stage, advanced incrementally; its parameters are fetched one iteration ahead
+      int gq_next = (kb0 * kTsBK) / group_size;
+      long long koff_next = (long long)kb0 * kTsBK;
+      auto fetch = [&](int kb) -> uint2 {
+        if (!live || kb >= num_kb) return make_uint2(0u, 0u);
+        return __ldg(sz + (size_t)n * Gq + gq_next);
+      };
+      uint2 p_cur = fetch(kb0);
+      for (int kb = kb0; kb < num_kb; kb += 2) {
+        const uint32_t it = it0 + (uint32_t)kb;
+        const uint32_t s = it % kTsStages, ph = (it / kTsStages) & 1u;
+        koff_next += 2 * kTsBK;
+        while (koff_next >= (long long)(gq_next + 1) * group_size) ++gq_next;
+        const uint2 p_next = fetch(kb + 2);
+        // scale planes and zero point of this stage's group
+        const __half2 sh2 = __half2half2(__ushort_as_half((unsigned short)(p_cur.x & 0xFFFFu)));
+        const __half2 sl2 = __half2half2(__ushort_as_half((unsigned short)(p_cur.x >> 16)));
+        const float zf = __half2float(__ushort_as_half((unsigned short)p_cur.y));
+        const __half2 zsub = __float2half2_rn(1024.f + zf);  // exact: |zero| <= 1024
+        const __half2 noff = __float2half2_rn(-(64.f + zf));
+        p_cur = p_next;
+        mbar_wait_relaxed(&sm->full[s], ph, 0);
+        const uint32_t* bq = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * kTsStageBytes + 2 * kXBytes);
+        uint32_t w[kTsBK / 8];
 #pragma unroll
-      for (int r = 0; r < kTsBK / 8; ++r) w[r] = bq[r * kWRows + t];
-      const uint32_t abase = lane_base + (uint32_t)s * kAStageCols;
+        for (int r = 0; r < kTsBK / 8; ++r) w[r] = bq[r * kWRows + t];
+        const uint32_t abase = lane_base + s * kAStageCols;
 #pragma unroll
-      for (int p = 0; p < kTsBK / 16; ++p) {  // two packed words = 16 K = one MMA K step = 8 TMEM columns per plane
-        uint32_t H[8], L[8];
+        for (int p = 0; p < kTsBK / 16; ++p) {  // two packed words = 16 K = one MMA K step = 8 TMEM columns per plane
+          uint32_t H[8], L[8];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const uint32_t lo32 = w[2 * p + i], hi32 = lo32 >> 8;
-          // 0x6400 | q = fp16(1024 + q);  0x6400 | (q << 4) = fp16(1024 + 16 q)
-          const __half2 v0 = u2h2(and_or<0x000F000Fu>(lo32, bias));  // k = 8r + (0, 4)
-          const __half2 v1 = u2h2(and_or<0x00F000F0u>(lo32, bias));  // k = 8r + (1, 5), times 16
-          const __half2 v2 = u2h2(and_or<0x000F000Fu>(hi32, bias));  // k = 8r + (2, 6)
-          const __half2 v3 = u2h2(and_or<0x00F000F0u>(hi32, bias));  // k = 8r + (3, 7), times 16
-          __half2 d[4];
-          d[0] = __hsub2(v0, zsub);        // (1024 + q) - (1024 + zero)           = q - zero, exact
-          d[1] = __hfma2(v1, k16, noff);   // (1024 + 16 q) / 16 - (64 + zero)     = q - zero, exact
-          d[2] = __hsub2(v2, zsub);
-          d[3] = __hfma2(v3, k16, noff);
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t lo32 = w[2 * p + i], hi32 = lo32 >> 8;
+            // 0x6400 | q = fp16(1024 + q);  0x6400 | (q << 4) = fp16(1024 + 16 q)
+            const __half2 v0 = u2h2(and_or<0x000F000Fu>(lo32, bias));  // k = 8r + (0, 4)
+            const __half2 v1 = u2h2(and_or<0x00F000F0u>(lo32, bias));  // k = 8r + (1, 5), times 16
+            const __half2 v2 = u2h2(and_or<0x000F000Fu>(hi32, bias));  // k = 8r + (2, 6)
+            const __half2 v3 = u2h2(and_or<0x00F000F0u>(hi32, bias));  // k = 8r + (3, 7), times 16
+            __half2 d[4];
+            d[0] = __hsub2(v0, zsub);        // (1024 + q) - (1024 + zero)           = q - zero, exact
+            d[1] = __hfma2(v1, k16, noff);   // (1024 + 16 q) / 16 - (64 + zero)     = q - zero, exact
+            d[2] = __hsub2(v2, zsub);
+            d[3] = __hfma2(v3, k16, noff);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __half2 hi = __hmul2(sh2, d[j]);                  // RN16(s_hi * d)
-            const __half2 tt = __hfma2(sh2, d[j], __hneg2(hi));     // s_hi * d - hi, exact
-            const __half2 lo = __hfma2(sl2, d[j], tt);              // + s_lo * d
-            H[4 * i + j] = h22u(hi);
-            L[4 * i + j] = h22u(lo);
+            for (int j = 0; j < 4; ++j) {
+              const __half2 hi = __hmul2(sh2, d[j]);                  // RN16(s_hi * d)
+              const __half2 tt = __hfma2(sh2, d[j], __hneg2(hi));     // s_hi * d - hi, exact
+              const __half2 lo = __hfma2(sl2, d[j], tt);              // + s_lo * d
+              H[4 * i + j] = h22u(hi);
+              L[4 * i + j] = h22u(lo);
+            }
           }
+          tc_st8(abase + 8 * p, H);
+          tc_st8(abase + 32 + 8 * p, L);
         }
-        tc_st8(abase + 8 * p, H);
-        tc_st8(abase + 32 + 8 * p, L);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->ready[s]);
       }
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->ready[s]);
     }
   } else if (warp >= 4) {
     // ================================================================== epilogue (8 warps)
@@ -285,65 +309,79 @@ gptq4_ts_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     const int e = threadIdx.x - 4 * 32;     // 0..255
     const int quarter = warp & 3;           // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;       // which 128 token columns
-    const int n = n0 + quarter * 32 + lane; // this thread's output feature
-    sm->rs[e] = (m0 + e < M) ? __ldg(rowscale + m0 + e) : 0.f;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    float acc[128];
-#pragma unroll
-    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 128);
-    for (int c = 0; c < num_chunks; ++c) {
-      mbar_wait(&sm->acc_full, (uint32_t)c & 1u);
-      tc_fence_after();
+    uint32_t cc = 0;  // chunk counter, continues across tiles
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * kTok;
+      const int n = (tile / tiles_m) * kWRows + quarter * 32 + lane;  // this thread's output feature
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // every epilogue warp finished reading rs[] of the previous tile
+      sm->rs[e] = (m0 + e < M) ? __ldg(rowscale + m0 + e) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float acc[128];
 #pragma unroll
-      for (int g = 0; g < 16; g += 2) {
-        uint32_t a[8], b[8];
-        tc_ld8(taddr + 8 * g, a);
-        tc_ld8(taddr + 8 * g + 8, b);
-        tc_wait_ld();
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int c = 0; c < num_chunks; ++c, ++cc) {
+        mbar_wait(&sm->acc_full, cc & 1u);
+        tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[8 * g + j] += __uint_as_float(a[j]);
-          acc[8 * g + 8 + j] += __uint_as_float(b[j]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->acc_empty);
-    }
-    if (n < N) {
-      const float cs = __ldg(colscale + n);
+        for (int g = 0; g < 16; g += 2) {
+          uint32_t a[8], b[8];
+          tc_ld8(taddr + 8 * g, a);
+          tc_ld8(taddr + 8 * g + 8, b);
+          tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 128; ++j) acc[j] *= cs;
-      if (!int_zero) {
-        // zero points with a fractional part: the MMA used q - rint(zero); subtract the residual
-        //   out = rs * (cs * acc - sum_g (zeros[n, g] - rint(zero) * scales[n, g]) * xsum[m, g])
-        int gq = 0;
-        long long kend = group_size;
-        for (int g = 0; g < G128; ++g) {
-          while ((long long)g * kGroup128 >= kend) { ++gq; kend += group_size; }
-          const float zi = __half2float(__ushort_as_half((unsigned short)__ldg(&sz[(size_t)n * Gq + gq].y)));
-          const float zr = -fmaf(-zi, __ldg(scales + (size_t)n * Gq + gq), __ldg(zeros + (size_t)n * Gq + gq));
-#pragma unroll
-          for (int j = 0; j < 128; ++j) {
-            const int m = m0 + half * 128 + j;
-            if (m < M) acc[j] = fmaf(zr, __ldg(xsum + (size_t)m * G128 + g), acc[j]);
+          for (int j = 0; j < 8; ++j) {
+            acc[8 * g + j] += __uint_as_float(a[j]);
+            acc[8 * g + 8 + j] += __uint_as_float(b[j]);
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->acc_empty);
       }
-      // out[m, n] += rs[m] * acc: 16 independent loads in flight, then 16 stores (a load-modify-store per element
-      // would serialise 128 global round trips: the compiler cannot prove that row j + 1 does not alias row j)
-      float* ocol = out + (size_t)(m0 + half * 128) * N + n;
-      const float* rsv = sm->rs + half * 128;
-      const int rows_here = min(128, M - (m0 + half * 128));
+      // the accumulator is free again: the MMAs of the next tile run while this tile is written out
+      if (n < N) {
+        const float cs = __ldg(colscale + n);
 #pragma unroll
-      for (int j0 = 0; j0 < 128; j0 += 16) {
-        float o[16];
+        for (int j = 0; j < 128; ++j) acc[j] *= cs;
+        if (!int_zero) {
+          // zero points with a fractional part: the MMA used q - rint(zero); subtract the residual
+          //   out = rs * (cs * acc - sum_g (zeros[n, g] - rint(zero) * scales[n, g]) * xsum[m, g])
+          int gq = 0;
+          long long kend = group_size;
+          for (int g = 0; g < G128; ++g) {
+            while ((long long)g * kGroup128 >= kend) { ++gq; kend += group_size; }
+            const float zi = __half2float(__ushort_as_half((unsigned short)__ldg(&sz[(size_t)n * Gq + gq].y)));
+            const float zr = -fmaf(-zi, __ldg(scales + (size_t)n * Gq + gq), __ldg(zeros + (size_t)n * Gq + gq));
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = (j0 + j < rows_here) ? __ldcg(ocol + (size_t)(j0 + j) * N) : 0.f;
+            for (int j = 0; j < 128; ++j) {
+              const int m = m0 + half * 128 + j;
+              if (m < M) acc[j] = fmaf(zr, __ldg(xsum + (size_t)m * G128 + g), acc[j]);
+            }
+          }
+        }
+        // out[m, n] += rs[m] * acc: 16 independent loads in flight, then 16 stores (a load-modify-store per element
+        // would serialise 128 global round trips: the compiler cannot prove that row j + 1 does not alias row j)
+        const float* rsv = sm->rs + half * 128;
+        const int rows_here = min(128, M - (m0 + half * 128));
+        if (out_h) {
+          const float bn = bias ? __ldg(bias + n) : 0.f;
+          __half* hcol = out_h + (size_t)(m0 + half * 128) * N + n;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j0 + j < rows_here) __stcg(ocol + (size_t)(j0 + j) * N, fmaf(rsv[j0 + j], acc[j0 + j], o[j]));
+          for (int j = 0; j < 128; ++j)
+            if (j < rows_here) hcol[(size_t)j * N] = __float2half_rn(fmaf(rsv[j], acc[j], bn));
+          continue;
+        }
+        float* ocol = out + (size_t)(m0 + half * 128) * N + n;
+#pragma unroll
+        for (int j0 = 0; j0 < 128; j0 += 16) {
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = (j0 + j < rows_here) ? __ldcg(ocol + (size_t)(j0 + j) * N) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j0 + j < rows_here) __stcg(ocol + (size_t)(j0 + j) * N, fmaf(rsv[j0 + j], acc[j0 + j], o[j]));
+        }
       }
     }
   }
@@ -376,14 +414,42 @@ static TsWorkspace ts_layout(long long M, long long K, long long N, long long Gq
   return w;
 }
 
+// fp16 activations: the hi plane IS the input (no row scaling needed: |x| <= 65504 and |w'| < 2^15 keep every product
+// inside fp32), copied with every 8 K permuted to (0, 4, 1, 5, 2, 6, 3, 7) to match the nibble pairs one LOP3 extracts;
+// xsum[m, g] = sum over the 128-K block (only read when some zero point has a fractional part).
+__global__ void __launch_bounds__(256) gptq_permute_f16_kernel(const __half* __restrict__ x, __half* __restrict__ a_hi,
+                                                               float* __restrict__ xsum, float* __restrict__ rowscale, int K,
+                                                               int G) {
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const __half* xr = x + (size_t)m * K;
+  if (tid == 0) rowscale[m] = 1.f;
+  const int nchunk = K >> 3;
+  for (int c0 = 0; c0 < nchunk; c0 += 256) {
+    const int c = c0 + tid;
+    float s = 0.f;
+    if (c < nchunk) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c * 8);
+      const __half* h = reinterpret_cast<const __half*>(&raw);
+      const __half p[8] = {h[0], h[4], h[1], h[5], h[2], h[6], h[3], h[7]};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += __half2float(h[j]);
+      *reinterpret_cast<uint4*>(a_hi + (size_t)m * K + c * 8) = *reinterpret_cast<const uint4*>(p);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((lane & 15) == 0 && (c >> 4) < G) xsum[(size_t)m * G + (c >> 4)] = s;
+  }
+}
+
 size_t gptq4_ts_workspace(long long M, long long K, long long N, int group_size) {
   if (K % 8 != 0 || N % 4 != 0 || group_size % kGroup128 != 0) return 0;
   return ts_layout(M, K, N, (K + group_size - 1) / group_size).total + 1024;
 }
 
+// x_h != nullptr: fp16 activations in, fp16 `out_h = bias + x @ W` out (sb200_gptq4_linear_f16); else the fp32 contract.
 int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
              long long K, long long N, long long KW, int group_size, int chunk_kb, void* workspace, size_t workspace_bytes,
-             cudaStream_t st) {
+             cudaStream_t st, const __half* x_h, __half* out_h, const float* bias) {
   const int Gq = (int)((K + group_size - 1) / group_size);
   const TsWorkspace w = ts_layout(M, K, N, Gq);
   unsigned char* ws = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
@@ -405,7 +471,12 @@ int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* sc
   SB_CUDA(cudaMemsetAsync(flag + 1, 0, sizeof(int), st));  // [1] need_lo, set by the split kernel
   gptq_ts_prepare_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(scales, zeros, (int)N, Gq, sz, cs, flag);
   SB_LAUNCHED();
-  if (const int rc = gptq_launch_split(x, a_hi, a_lo, xsum, rowscale, flag + 1, M, (int)K, G128, st)) return rc;
+  if (x_h) {
+    gptq_permute_f16_kernel<<<(unsigned)M, 256, 0, st>>>(x_h, a_hi, xsum, rowscale, (int)K, G128);
+    SB_LAUNCHED();
+  } else if (const int rc = gptq_launch_split(x, a_hi, a_lo, xsum, rowscale, flag + 1, M, (int)K, G128, st)) {
+    return rc;
+  }
 
   CUtensorMap map_hi, map_lo, map_q;
   const bool ok = make_map_2d(&map_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a_hi, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2,
@@ -421,9 +492,10 @@ int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* sc
   const size_t smem = (size_t)kTsStages * kTsStageBytes + sizeof(TsSmem) + 1024;
   static std::atomic<int> attr_done[64];
   SB_CUDA(ensure_dyn_smem(gptq4_ts_kernel, (int)smem, attr_done));
-  const dim3 grid((unsigned)((M + kTok - 1) / kTok), (unsigned)((N + kWRows - 1) / kWRows));
+  const long long num_tiles = ((M + kTok - 1) / kTok) * ((N + kWRows - 1) / kWRows);
+  const unsigned grid = (unsigned)(num_tiles < sm_count() ? num_tiles : sm_count());  // persistent: one CTA per SM
   gptq4_ts_kernel<<<grid, kTsThreads, smem, st>>>(map_hi, map_lo, map_q, out, scales, zeros, xsum, rowscale, sz, cs, flag, (int)M,
-                                                  (int)K, (int)N, Gq, G128, group_size, chunk_kb);
+                                                  (int)K, (int)N, Gq, G128, group_size, chunk_kb, out_h, bias);
   SB_LAUNCHED();
   return SB200_OK;
 }

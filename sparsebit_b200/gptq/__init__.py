@@ -11,3 +11,4 @@ from .quant_linear import (  # noqa: F401
     pack_intweight,
     pack_rows,
 )
+from .streaming import LayerStreamer  # noqa: F401,E402

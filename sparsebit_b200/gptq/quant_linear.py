@@ -151,6 +151,16 @@ class QuantLinear(nn.Module):
         self.qweight = pack_intweight(q.to(torch.int64).t().contiguous(), self.bit)
 
     def forward(self, x):
+        if self.bit == 4 and x.is_cuda and x.dtype == torch.float16 and self.qweight.is_cuda and not torch.is_grad_enabled():
+            # the model path (fp16 activations): one library call, no per-call casts of x / scales / zeros / bias and no
+            # fp32 copy of the result (the reference casts all of them every forward, utils/quant.py:262-278)
+            from .. import ops
+
+            if getattr(self, "_f32_tables", None) is None or self._f32_tables[0].device != x.device:
+                self._f32_tables = (self.scales.float().contiguous().to(x.device), self.zeros.float().contiguous().to(x.device),
+                                    self.bias.float().contiguous().to(x.device))
+            sc, zr, bs = self._f32_tables
+            return ops.gptq4_linear_f16(x.contiguous(), self.qweight, sc, zr, bs, 0 if self.groupsize == -1 else self.groupsize)
         # fp32 math like the reference (utils/quant.py:262-278), result cast back to x.dtype
         y = QuantMatmul.apply(x.float(), self.qweight, self.scales.float(), self.zeros.float(), self.bias.float(),
                               self.groupsize, self.bit)

@@ -118,6 +118,60 @@ def qdq_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=None, roundin
     return gx, gs, gzp
 
 
+# ----------------------------------------------------------------------------- multi-tensor weight QDQ
+class _QdqTensorDesc(ctypes.Structure):  # include/sparsebit_b200.h sb200_qdq_tensor_desc
+    _fields_ = [("x", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("zero_point", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("outer", ctypes.c_int64), ("channels", ctypes.c_int64), ("inner", ctypes.c_int64),
+                ("qmin", ctypes.c_int), ("qmax", ctypes.c_int)]
+
+
+class QdqMulti:
+    """(mask-apply +) per-channel QDQ of many tensors in ONE launch (sb200_qdq_multi_plan / _run).
+
+    ``items``: iterable of dicts ``x, scale, zero_point, qmin, qmax`` and optional ``mask`` (bool / uint8),
+    ``out`` (default: a new tensor), ``ch_axis`` (default 0).  The plan keeps references to every tensor; ``run()``
+    re-reads their CURRENT contents (the weights of a training step), one kernel launch per call."""
+
+    def __init__(self, items):
+        lib = _lib.load()
+        self.items = []
+        descs = []
+        for it in items:
+            x = _req(it["x"], "data")
+            scale = _req(it["scale"].reshape(-1), "scale")
+            zp = _req(it["zero_point"].reshape(-1), "zero_point")
+            outer, c, inner = channel_geometry(x.shape, it.get("ch_axis", 0))
+            if scale.numel() != c or zp.numel() != c:
+                raise SparsebitB200Error(f"per-channel qparams need {c} elements (got {scale.numel()}, {zp.numel()})")
+            mask = it.get("mask")
+            if mask is not None:
+                if mask.dtype not in (torch.bool, torch.uint8) or mask.shape != x.shape or not mask.is_contiguous():
+                    raise SparsebitB200Error("mask must be a contiguous bool / uint8 tensor shaped like the data")
+            out = it.get("out")
+            out = torch.empty_like(x) if out is None else _req(out, "out")
+            self.items.append((x, mask, scale, zp, out))
+            descs.append(_QdqTensorDesc(x.data_ptr(), mask.data_ptr() if mask is not None else None, scale.data_ptr(),
+                                        zp.data_ptr(), out.data_ptr(), outer, c, inner, int(it["qmin"]), int(it["qmax"])))
+        if not descs:
+            raise SparsebitB200Error("QdqMulti: no tensors")
+        self.device = self.items[0][0].device
+        self.count = len(descs)
+        arr = (_QdqTensorDesc * self.count)(*descs)
+        self.table = torch.empty(int(lib.sb200_qdq_multi_table_bytes(self.count)), dtype=torch.uint8, device=self.device)
+        rows = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(lib.sb200_qdq_multi_plan(arr, self.count, self.table.data_ptr(), self.table.numel(), ctypes.byref(rows),
+                                           torch.cuda.current_stream(self.device).cuda_stream))
+        self.total_rows = rows.value
+        self.outputs = [it[4] for it in self.items]
+
+    def run(self):
+        with torch.cuda.device(self.device):
+            check(_lib.load().sb200_qdq_multi_run(self.table.data_ptr(), self.count, self.total_rows,
+                                                  torch.cuda.current_stream(self.device).cuda_stream))
+        return self.outputs
+
+
 # ----------------------------------------------------------------------------- row moments
 MOMENTS = 5  # sum x, sum x^2, sum |x|, sum |x - c|, sum (x - c)^2
 
@@ -319,6 +373,20 @@ def mask_gt(w, thresh):
     return mask
 
 
+def mask_rows_gt(score, thresh, shape):
+    """Float mask of ``shape`` = [rows, ...]: row r is all ones if score[r] > thresh else all zeros."""
+    lib = _lib.load()
+    _req(score, "score"), _req(thresh, "thresh")
+    rows = int(shape[0])
+    if score.numel() != rows:
+        raise SparsebitB200Error("mask_rows_gt: one score per row expected")
+    mask = torch.empty(tuple(shape), dtype=torch.float32, device=score.device)
+    with torch.cuda.device(score.device):
+        check(lib.sb200_mask_rows_gt(score.data_ptr(), thresh.data_ptr(), mask.data_ptr(), rows, mask.numel() // rows,
+                                     _stream(score)))
+    return mask
+
+
 def mask_apply(w, mask, out=None):
     lib = _lib.load()
     _req(w, "weight")
@@ -389,6 +457,29 @@ def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0, impl=None, chunk_
             check(lib.sb200_gptq4_matmul_ex(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(),
                                             zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size), ctypes.byref(opts),
                                             ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x)))
+    return out
+
+
+def gptq4_linear_f16(x, qweight, scales, zeros, bias=None, group_size=0):
+    """fp16 activations in, fp16 ``bias + x @ dequant(qweight)`` out, no eager casts (sb200_gptq4_linear_f16)."""
+    lib = _lib.load()
+    _req(x, "inp1", torch.float16), _req(scales, "scales"), _req(zeros, "zeros"), _req(qweight, "inp2", torch.int32)
+    if bias is not None:
+        _req(bias, "bias")
+    k = x.shape[-1]
+    m = x.numel() // k
+    n = qweight.shape[1]
+    out = torch.empty(x.shape[:-1] + (n,), dtype=torch.float16, device=x.device)
+    ws_bytes = int(lib.sb200_gptq4_linear_f16_workspace_bytes(m, k, n, int(group_size)))
+    key = (x.device, torch.cuda.current_stream(x.device).cuda_stream, "f16")
+    ws = _gptq_ws.get(key)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _gptq_ws[key] = ws
+    with torch.cuda.device(x.device):
+        check(lib.sb200_gptq4_linear_f16(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                         scales.data_ptr(), zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size), ws.data_ptr(),
+                                         ws_bytes, _stream(x)))
     return out
 
 

@@ -28,7 +28,9 @@ class DataCache:
         self._batches = 0
         self._batch_size = 0
 
-    def update(self, data):
+    def update(self, data, alias_ok=False):
+        """``alias_ok``: the caller guarantees that nobody writes to ``data`` before ``calc_qparams`` (the calibration
+        runner passes it for operators that are not in-place), so a retained batch may share its storage."""
         x = data.detach()
         src_ptr = x.data_ptr() if x.is_cuda else None
         if not x.is_cuda:
@@ -47,7 +49,7 @@ class DataCache:
             # a retained batch must not alias the caller's tensor: the streaming pre-hook hands over the live
             # activation, which an in-place operator (ReLU(inplace=True), the torchvision default) overwrites
             # before the observer's second pass.  (The reference is immune because it copies to the CPU.)
-            if src_ptr is not None and x.data_ptr() == src_ptr:
+            if not alias_ok and src_ptr is not None and x.data_ptr() == src_ptr:
                 x = x.clone()
             self._tensors.append(x)
         if self._owner is not None:

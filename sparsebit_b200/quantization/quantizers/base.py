@@ -41,9 +41,9 @@ class Quantizer(nn.Module, abc.ABC):
             warnings.warn("used bit==0 to disable quantizer is deprecated, please use a flag: QUANTIZER.DISABLE")
 
     # ---- calibration -----------------------------------------------------------------
-    def update_observer(self, x):
+    def update_observer(self, x, alias_ok=False):
         self.dims = x.dim()
-        self.observer.data_cache.update(x.detach())
+        self.observer.data_cache.update(x.detach(), alias_ok=alias_ok)
 
     def _store_qparams(self, scale, zero_point):
         self.scale = self._broadcast_qparams(scale)

@@ -17,6 +17,6 @@ class Quantizer(BaseQuantizer):
     def _forward(self, x, scale, zero_point):
         return STE.apply(_normalise(x), self.scale, self.zero_point, self.qdesc, self.backend)
 
-    def update_observer(self, x):
+    def update_observer(self, x, alias_ok=False):
         self.dims = x.dim()
-        self.observer.data_cache.update(_normalise(x.detach()))
+        self.observer.data_cache.update(_normalise(x.detach()), alias_ok=True)  # the normalised copy is private

@@ -116,8 +116,11 @@ class CalibrationRunner:
             self._seen.add(id(module))
             self._order.append(module)
         if self.streaming and _live(module.input_quantizer):
+            q = module.input_quantizer
+            # a retained batch may alias the live activation unless this operator overwrites its input
+            kw = {"alias_ok": not getattr(module, "inplace", False)} if hasattr(q, "calc_qparams_steps") else {}
             for x in _tensors_of(args):
-                module.input_quantizer.update_observer(x.detach())
+                q.update_observer(x.detach(), **kw)
 
     def _remove_hooks(self):
         for h in self._handles:
@@ -163,7 +166,7 @@ class CalibrationRunner:
                 todo.append(module.input_quantizer)
             wq = module.weight_quantizer
             if wq is not None:
-                wq.update_observer(module.weight)
+                wq.update_observer(module.weight, **({"alias_ok": True} if hasattr(wq, "calc_qparams_steps") else {}))
                 todo.append(wq)
         sbdist.drive_all([_qparams_steps(q) for q in todo])
         for q in feature:
@@ -174,7 +177,7 @@ class CalibrationRunner:
         wq = module.weight_quantizer
         if wq is None:
             return
-        wq.update_observer(module.weight)
+        wq.update_observer(module.weight, **({"alias_ok": True} if hasattr(wq, "calc_qparams_steps") else {}))
         wq.calc_qparams()
 
     # ------------------------------------------------------------------ layer-wise replay (device resident)
@@ -208,7 +211,9 @@ class CalibrationRunner:
                 for inp in node.all_input_nodes:
                     for x in float_env[inp]:
                         if isinstance(x, torch.Tensor):
-                            quant_opr.input_quantizer.update_observer(x)
+                            # stored activations are never written to (in-place operators get private copies)
+                            q = quant_opr.input_quantizer
+                            q.update_observer(x, **({"alias_ok": True} if hasattr(q, "calc_qparams_steps") else {}))
                 quant_opr.input_quantizer.calc_qparams()
                 quant_opr.input_quantizer.observer.data_cache.reset()
             float_env[node] = self._run_node(node, module, float_env, n_batches)

@@ -88,3 +88,37 @@ class SLinear(SparseOpr):
     def forward(self, x_in):
         weight, bias = self._masked()
         return F.linear(x_in, weight, bias)
+
+
+class SBatchNorm2d(SparseOpr):
+    """sparse/modules/normalization.py:8-28: after a structurally pruned convolution the reference multiplies the
+    BatchNorm output by the [1, C, 1, 1] filter mask -- a full extra pass over the activation (8 B/elem).  A {0, 1}
+    channel mask commutes with the affine part of the normalisation, bn(x) * mask = bn(x; gamma * mask, beta * mask),
+    so here the mask is folded into the C affine parameters and the pass disappears (identical results for finite
+    activations; gradients reach gamma / beta through the same product)."""
+
+    def __init__(self, org_module, config=None):
+        assert isinstance(org_module, nn.BatchNorm2d)
+        super().__init__()
+        self.module = org_module
+        self.weight = None  # not a prunable weight: SparseOpr.calc_mask is overridden below
+        self.register_buffer("mask", torch.ones(1, org_module.num_features, 1, 1))
+
+    def calc_mask(self, pre_mask=None):
+        if self.sparser is not None and self.sparser.type == "structed" and self.sparser.strategy == "l1norm" and pre_mask is not None:
+            self.mask.data.copy_(pre_mask.reshape(self.mask.shape).to(self.mask))
+        return None
+
+    def forward(self, x_in):
+        bn = self.module  # same bookkeeping as torch.nn.modules.batchnorm._BatchNorm.forward
+        m = self.mask.reshape(-1).to(x_in.device)
+        weight = (bn.weight if bn.weight is not None else torch.ones_like(m)) * m
+        bias = bn.bias * m if bn.bias is not None else None
+        factor = 0.0 if bn.momentum is None else bn.momentum
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            factor = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
+        batch_stats = bn.training or (bn.running_mean is None and bn.running_var is None)
+        keep_running = not bn.training or bn.track_running_stats
+        return F.batch_norm(x_in, bn.running_mean if keep_running else None, bn.running_var if keep_running else None,
+                            weight, bias, batch_stats, factor, bn.eps)

@@ -4,8 +4,11 @@ unstructed: the reference fully sorts |w| to read ONE order statistic (``sorted[
 n-1)]``) and masks ``|w| > thresh`` (strict: ties at the threshold are pruned, Q12).  Here the
 threshold is the exact k-th smallest |w| from a 3-pass radix select on the device
 (``sb200_select_*`` with key = |x|) followed by ``sb200_mask_gt`` -- same element, same mask, no
-sort.  structed: per-filter L1 sums are tiny ([Cout] values); the filter ranking stays in torch
-and the mask is built without the reference's per-index CPU round trips (:36-40).
+sort.  structed (:27-40): the per-filter L1 norms are one pass of the row-moments kernel (``sb200_observe_moments``,
+fp64 sums), the cut is the exact (pruned - 1)-th smallest norm from the same radix select, and the float mask is
+written by ``sb200_mask_rows_gt`` -- no ``abs().sum()`` / ``torch.sort`` / per-index CPU round trips.  The ranking
+equals the reference's whenever two filters' norms differ by more than its fp32 summation error; filters that tie
+with the cut are pruned together.
 """
 import torch
 
@@ -33,12 +36,13 @@ class Sparser(BaseSparser):
             thresh = ops.kth_value(w.reshape(-1), k, key_mode=1)
             mask = ops.mask_gt(w, thresh)
         elif self.type == "structed":
-            l1 = w.reshape(w.shape[0], -1).abs().sum(dim=1)
-            order = torch.sort(l1, dim=0).indices
-            pruned = order[: int(w.shape[0] * self.ratio)]
-            keep = torch.ones(w.shape[0], dtype=w.dtype, device=w.device)
-            keep[pruned] = 0
-            mask = keep.reshape([-1] + [1] * (w.dim() - 1)).expand_as(w).contiguous()
+            pruned = int(w.shape[0] * self.ratio)
+            if pruned == 0:
+                return torch.ones_like(x)
+            rows = w.reshape(w.shape[0], -1)
+            l1 = ops.moments_update(rows, ops.moments_new(rows.shape[0], w.device))[:, 2].to(torch.float32).contiguous()
+            thresh = ops.kth_value(l1, pruned - 1, key_mode=0)
+            mask = ops.mask_rows_gt(l1, thresh, w.shape)
         else:
             raise NotImplementedError(self.type)
         return mask.to(x.device)

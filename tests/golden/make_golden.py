@@ -493,8 +493,55 @@ def gen_bwd():
     save("bwd", **out)
 
 
+def gen_sparse_structured():
+    """Structured (filter) pruning, sparse/sparsers/l1norm.py:27-40, and the SConv2d -> SBatchNorm2d mask hand-over
+    (sparse/modules/conv.py:22-37, normalization.py:15-28) from the unmodified reference on CPU."""
+    import torch.nn as nn
+    from sparsebit.sparse.modules import SBatchNorm2d, SConv2d
+    from sparsebit.sparse.sparsers import build_sparser
+
+    g = torch.Generator().manual_seed(31337)
+    out, cases = {}, []
+    for name, shape, ratio in [("conv_r50", (16, 4, 3, 3), 0.5), ("conv_r30", (10, 3, 3, 3), 0.3), ("lin_r25", (12, 33), 0.25),
+                               ("conv_r05", (8, 2, 1, 1), 0.05)]:
+        cfg = R._CfgNode({"SPARSER": {"TYPE": "structed", "STRATEGY": "l1norm", "RATIO": ratio}})
+        sp = build_sparser(cfg, opr=None)
+        w = torch.randn(shape, generator=g)
+        mask = sp.calc_mask(w)
+        cases.append(name)
+        out[name + "_w"] = w.numpy()
+        out[name + "_mask"] = mask.numpy()
+        out[name + "_ratio"] = np.array(ratio)
+    out["cases"] = np.array(cases)
+    # conv -> bn pair: the conv's filter mask is handed to the following SBatchNorm2d (sparse_model.py calc_params order)
+    torch.manual_seed(5)
+    conv, bn = nn.Conv2d(3, 8, 3, padding=1), nn.BatchNorm2d(8)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(8, generator=g))
+        bn.bias.copy_(torch.randn(8, generator=g))
+        bn.running_mean.copy_(torch.randn(8, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(8, generator=g) + 0.5)
+    cfg = R._CfgNode({"SPARSER": {"TYPE": "structed", "STRATEGY": "l1norm", "RATIO": 0.5}})
+    sconv, sbn = SConv2d(conv, cfg), SBatchNorm2d(bn, cfg)
+    sconv.build_sparser(cfg)
+    sbn.build_sparser(cfg)
+    pre = sconv.calc_mask()
+    sbn.calc_mask(pre)
+    x = torch.randn(2, 3, 6, 6, generator=g)
+    sconv.eval(), sbn.eval()
+    with torch.no_grad():
+        y = sbn(sconv(x))
+    for k, v in conv.state_dict().items():
+        out["pair_conv_" + k] = v.numpy()
+    for k, v in bn.state_dict().items():
+        out["pair_bn_" + k] = v.numpy()
+    out["pair_x"], out["pair_y"], out["pair_bn_mask"] = x.numpy(), y.numpy(), sbn.mask.numpy()
+    save("sparse_structured", **out)
+
+
 GENERATORS = {"qdq": gen_qdq, "observers": gen_observers, "sparse": gen_sparse, "gptq": gen_gptq,
-              "next_rows": gen_next_rows, "calibration": gen_calibration, "bwd": gen_bwd}
+              "next_rows": gen_next_rows, "calibration": gen_calibration, "bwd": gen_bwd,
+              "sparse_structured": gen_sparse_structured}
 
 if __name__ == "__main__":
     torch.set_num_threads(4)

@@ -32,7 +32,7 @@ def test_version_and_variant_validation():
     assert lib.sb200_set_variant(0) == 0
     assert lib.sb200_set_variant(7) != 0
     assert b"variant" in lib.sb200_last_error()
-    assert lib.sb200_gptq4_set_impl(4) != 0
+    assert lib.sb200_gptq4_set_impl(5) != 0
     assert lib.sb200_gptq4_set_impl(0) == 0
 
 

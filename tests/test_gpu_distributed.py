@@ -69,6 +69,38 @@ def _calibrate(rank, world, port, errq):
                 assert _bits_equal(q.observer.max_val.reshape(-1).cpu().numpy(), np.reshape(mx, -1)), (obs, scheme)
             assert _bits_equal(scale.reshape(-1).cpu().numpy(), np.reshape(es, -1)), (obs, scheme)
             assert _bits_equal(zp.reshape(-1).cpu().numpy(), np.reshape(ez, -1)), (obs, scheme)
+        # ---- the same five quantizers (+ ACIQ-laplace, LSQ, MovingAverage) finished in ONE lockstep sweep: their
+        # statistics cross the ranks in one packed MAX and one packed SUM all-reduce per round
+        specs = [("minmax", "per-tensor-affine", "uniform"), ("minmax", "per-channel-symmetric", "uniform"),
+                 ("percentile", "per-tensor-symmetric", "uniform"), ("mse", "per-tensor-symmetric", "uniform"),
+                 ("kl_histogram", "per-tensor-symmetric", "uniform"), ("aciq", "per-tensor-symmetric", "uniform"),
+                 ("minmax", "per-tensor-symmetric", "lsq"), ("moving_average", "per-tensor-affine", "uniform")]
+
+        def build_all():
+            qs = []
+            for obs, scheme, qtype in specs:
+                cfg = sbcfg.quantizer_config(scheme, 8, "feature", obs, "NLC", alpha=1e-3, qtype=qtype, aciq_distribution="LAPLACE")
+                q = build_quantizer(cfg)
+                q.set_backend(Backend.VIRTUAL)
+                for b in mine:
+                    q.update_observer(torch.from_numpy(b).to(dev))
+                qs.append(q)
+            return qs
+
+        sbdist.collectives(reset=True)
+        one_by_one = [tuple(t.detach().clone() for t in q.calc_qparams()) for q in build_all()]
+        n_single = sbdist.collectives(reset=True)
+        packed = [tuple(t.detach().clone() for t in r) for r in sbdist.drive_all([q.calc_qparams_steps() for q in build_all()])]
+        n_packed = sbdist.collectives(reset=True)
+        for (s1, z1), (s2, z2), spec in zip(one_by_one, packed, specs):
+            assert torch.equal(s1, s2) and torch.equal(z1, z2), spec
+        # round 1: MAX (7 running min/max states) + SUM (percentile pass 0) + gather; rounds 2, 3: SUM
+        assert n_packed == {"max": 1, "sum": 3, "gather": 1}, n_packed
+        assert n_single["max"] >= 6 and n_single["sum"] >= 8, n_single
+        # ACIQ-laplace / LSQ statistics now cover the WHOLE set (fp64 moments are summed across ranks)
+        whole = np.concatenate([b.reshape(-1) for b in everything]).astype(np.float64)
+        lsq_scale = 2 * np.abs(whole).mean() / np.sqrt(127)
+        assert abs(float(packed[6][0].reshape(-1)[0]) - lsq_scale) <= 1e-6 * lsq_scale
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:  # surface the failure in the parent

@@ -23,7 +23,7 @@ def _run(x, qw, bias, scales, zeros, gs):
     return y.cpu().numpy()
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 0, 4])  # small-M path (HMMA streaming kernel where N % 4 == 0), auto, scalar kernel
 def test_golden_known_answers(golden, impl):
     g = golden("gptq")
     _lib.load().sb200_gptq4_set_impl(impl)
@@ -56,11 +56,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("impl", [0, 4])
 @pytest.mark.parametrize("bshape,k,n,gs", CASES)
-def test_vs_fp64_oracle(bshape, k, n, gs):
+def test_vs_fp64_oracle(bshape, k, n, gs, impl):
     rng = np.random.default_rng(k + n + len(bshape))
     x, qw, bias, scales, zeros = _make_case(rng, bshape, k, n, gs)
-    y = _run(x, qw, bias, scales, zeros, gs)
+    y = _run_impl(x, qw, bias, scales, zeros, gs, impl=impl)
     exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, x.shape[:-1] + (n,)), scales, zeros, 0 if gs == -1 else gs)
     np.testing.assert_allclose(y, exp, **TOL)
 
@@ -108,6 +109,33 @@ def _run_impl(x, qw, bias, scales, zeros, gs, impl, chunk_k=0):
     y = t(np.broadcast_to(bias, x.shape[:-1] + (qw.shape[1],)).copy())
     ops.gptq4_matmul(t(x), t(qw), y, t(scales), t(zeros), 0 if gs == -1 else gs, impl=impl, chunk_k=chunk_k)
     return y.cpu().numpy()
+
+
+# warp-level HMMA streaming kernel (impl 1 with N % 4 == 0, gptq_decode.cu): 1 / 8 / 9 / 16 / 17 / 32 / 33 / 70 tokens (the
+# three token-block variants and the multi-pass loop), K not a multiple of 128 or 32, ragged feature blocks, fp32 and
+# fp16-exact activations, outliers, non-integer zero points
+DECODE_CASES = [(1, 4096, 4096, 128), (8, 1024, 512, 128), (9, 1024, 260, 128), (16, 2048, 1028, 256), (17, 512, 132, 128),
+                (32, 1536, 384, 384), (33, 1000, 256, -1), (70, 328, 64, -1), (1, 11008, 4096, 128), (5, 6656, 2516, -1)]
+
+
+@pytest.mark.parametrize("m,k,n,gs", DECODE_CASES)
+@pytest.mark.parametrize("fp16_acts", [False, True])
+def test_decode_hmma_path_vs_fp64_oracle(m, k, n, gs, fp16_acts):
+    rng = np.random.default_rng(13 * k + n + m)
+    x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, gs)
+    if fp16_acts:
+        x = x.astype(np.float16).astype(np.float32)
+    else:
+        x[0, :3] = [2.5e4, -6e4, 1e-7]  # per-token power-of-two scaling
+    if m > 1:
+        zeros = (zeros + 0.21 * scales).astype(np.float32)  # fractional zero points: the affine part is applied in fp32
+    y = _run_impl(x, qw, bias, scales, zeros, gs, impl=1)
+    exp = ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (m, n)), scales, zeros, 0 if gs == -1 else gs)
+    rows = list(range(1, m)) if not fp16_acts else list(range(m))
+    if rows:
+        np.testing.assert_allclose(y[rows], exp[rows], **TOL)
+    if not fp16_acts:  # the outlier row: bounded by the row magnitude (an fp32 result cannot do better)
+        np.testing.assert_array_less(np.abs(y[0] - exp[0]), 1e-5 + 1e-5 * max(1.0, np.abs(exp[0]).max()))
 
 
 # tensor-memory-operand kernel (impl 3, gptq_ts.cu): ragged token / feature tiles, odd numbers of 64-K stages,
@@ -208,6 +236,25 @@ def test_tcgen05_general_zero_points_fall_back_to_affine_epilogue():
     np.testing.assert_allclose(y, exp, **TOL)
 
 
+@pytest.mark.parametrize("m,k,n,gs", [(5, 1024, 512, 128), (300, 1024, 520, 128), (1024, 2048, 1028, 256), (777, 512, 260, -1)])
+def test_linear_f16_entry_point(m, k, n, gs):
+    """sb200_gptq4_linear_f16: fp16 activations in, fp16 ``bias + x @ W`` out without eager casts -- equals the fp32
+    entry point's result rounded to fp16 (up to one fp16 ulp where the fp32 results differ in the last bits)."""
+    from sparsebit_b200 import ops
+
+    rng = np.random.default_rng(m + k)
+    x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, gs)
+    xh = x.astype(np.float16)
+    g = 0 if gs == -1 else gs
+    y16 = ops.gptq4_linear_f16(t(xh), t(qw), t(scales), t(zeros), t(bias), g).cpu().numpy()
+    assert y16.dtype == np.float16 and y16.shape == (m, n)
+    exp = ogptq.dequant_matmul(xh.astype(np.float32), qw, np.broadcast_to(bias, (m, n)), scales, zeros, g)
+    ulp = np.abs(exp).astype(np.float16).astype(np.float32) * 2.0**-10 + 2.0**-24
+    assert np.all(np.abs(y16.astype(np.float64) - exp) <= 0.51 * ulp + 1e-5 * (1 + np.abs(exp)))
+    y_nobias = ops.gptq4_linear_f16(t(xh), t(qw), t(scales), t(zeros), None, g).cpu().numpy().astype(np.float32)
+    np.testing.assert_allclose(y_nobias, exp - bias, rtol=2e-3, atol=2e-3)
+
+
 def test_tcgen05_forced_on_unsupported_shape_is_an_error():
     lib = _lib.load()
     rng = np.random.default_rng(1)
@@ -232,7 +279,10 @@ def test_quant_linear_module_matches_dense_linear():
         x = torch.randn(b, k)
         gt = layer.to(dev())(x.to(dev()))
         torch.testing.assert_close(ql.to(dev())(x.to(dev())), gt, **TOL)
-        assert ql(x.to(dev()).half()).dtype == torch.float16
+        with torch.no_grad():
+            yh = ql(x.to(dev()).half())  # fp16 model path: sb200_gptq4_linear_f16, no casts
+        assert yh.dtype == torch.float16
+        torch.testing.assert_close(yh.float(), layer(x.to(dev()).half().float()), rtol=2e-3, atol=2e-3)
 
 
 def test_linearity_and_accumulate_contract_at_llama_shape():
@@ -264,3 +314,42 @@ def test_argument_checks():
         cuda_kernel.vecquant4matmul(x[0, :], qw, y[0], s, s)
     with pytest.raises(RuntimeError, match="out_channel"):
         cuda_kernel.vecquant4matmul(x, qw, torch.zeros(4, 9, device=dev()), s, s)
+
+
+def test_layer_streaming_equals_resident_execution():
+    """LayerStreamer (the reference's single_device_mode, llama_wrapper.py:848-924): packed weights stream from pinned host
+    memory into two device slots, one layer ahead of the compute; outputs equal the fully resident model and only two layers' worth of packed weights are on the device."""
+    from sparsebit_b200.gptq import LayerStreamer
+
+    torch.manual_seed(0)
+
+    class Block(torch.nn.Module):
+        def __init__(self, k, h):
+            super().__init__()
+            self.up, self.down = QuantLinear(k, h, 4, 128), QuantLinear(h, k, 4, 128)
+            for ql, (i, o) in ((self.up, (k, h)), (self.down, (h, k))):
+                lin = torch.nn.Linear(i, o)
+                s, z = find_params_int4(lin.weight.data, 128)
+                ql.pack(lin, s, z)
+
+        def forward(self, x):
+            return x + self.down(torch.relu(self.up(x)))
+
+    blocks = [Block(256, 512) for _ in range(5)]
+    x = torch.randn(7, 256, device=dev())
+    import copy
+
+    resident = [copy.deepcopy(b).to(dev()) for b in blocks]
+    with torch.no_grad():
+        ref = x
+        for b in resident:
+            ref = b(ref)
+        streamer = LayerStreamer(blocks, dev())
+        out1 = streamer(x)
+        out2 = streamer(x)  # slots are reused across forwards
+    # (split-K partial sums meet in fp32 atomics: equal up to the summation order)
+    torch.testing.assert_close(out1, ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out2, ref, rtol=1e-5, atol=1e-5)
+    per_layer = sum(m.qweight.numel() for m in resident[0].modules() if isinstance(m, QuantLinear)) * 4
+    assert streamer.resident_bytes() == 2 * per_layer
+    assert all(m.qweight.numel() == 0 for b in blocks for m in b.modules() if isinstance(m, QuantLinear))

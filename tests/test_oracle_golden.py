@@ -119,6 +119,44 @@ def test_torch_port_matches_reference(golden):
         assert _eq_bits(y.numpy(), g[name + "_y"]), name
 
 
+def test_torch_port_observers_and_sparser_match_reference(golden):
+    """The observer / sparser CPU op chains bench.py times as ``cpu_baselines`` (oracle/torch_port.py) reproduce the
+    reference's per-tensor results: same min/max, same MSE candidate, same k-th values, same KL threshold, same mask."""
+    import torch
+
+    from oracle import torch_port
+
+    g = golden("observers")
+    for name in g["cases"]:
+        qmin, qmax, ch_axis, perch, sym, bit = (int(v) for v in g[name + "_meta"])
+        if perch:
+            continue
+        xs = [torch.from_numpy(g[f"{name}_x{i}"]) for i in range(int(g[name + "_nb"]))]
+        if name.startswith("minmax"):
+            mn, mx = torch_port.minmax_observer_cpu(xs)
+            assert float(mn) == float(g[name + "_min"].reshape(-1)[0]) and float(mx) == float(g[name + "_max"].reshape(-1)[0])
+            s, z = torch_port.calc_qparams_with_minmax_cpu(mn, mx, qmin, qmax, bool(sym))
+        elif name.startswith("mse"):
+            s, z = torch_port.mse_observer_cpu(xs, qmin, qmax, bool(sym))
+        elif name.startswith("pct"):
+            mn, mx = torch_port.percentile_observer_cpu(xs, float(g[name + "_alpha"]))
+            assert float(mn) == float(g[name + "_min"].reshape(-1)[0]) and float(mx) == float(g[name + "_max"].reshape(-1)[0])
+            s, z = torch_port.calc_qparams_with_minmax_cpu(mn, mx, qmin, qmax, bool(sym))
+        else:
+            mn, mx = torch_port.kl_observer_cpu(xs, bit)
+            np.testing.assert_allclose([mn, mx], [g[name + "_min"].reshape(-1)[0], g[name + "_max"].reshape(-1)[0]], rtol=1e-6)
+            continue
+        assert _eq_bits(np.float32(s).reshape(-1), g[name + "_scale"].reshape(-1)), name
+        assert _eq_bits(np.float32(z).reshape(-1), g[name + "_zp"].reshape(-1)), name
+    g = golden("sparse")
+    for name in g["cases"]:
+        ratio = float(g[name + "_ratio"])
+        if ratio == 0.0:
+            continue
+        m = torch_port.l1_unstructured_mask_cpu(torch.from_numpy(g[name + "_w"]), ratio)
+        assert np.array_equal(m.numpy(), g[name + "_mask"].astype(bool)), name
+
+
 def test_c_restatement_matches_reference(golden):
     """oracle/c/libsb_oracle.so (plain C, -ffp-contract=off) == the reference's outputs."""
     import ctypes
