@@ -142,6 +142,25 @@ int sb200_observe_minmax_perchannel(const float* x, int64_t outer, int64_t chann
 int sb200_minmax_read(const uint32_t* state, int64_t channels, float* out_min, float* out_max,
                       void* stream);
 
+/* qparams of MANY MinMax observers in one launch: running state -> min, max, scale, zero_point
+ * (observers/minmax.py:14-25 + Observer.calc_qparams_with_minmax, observers/base.py:63-79; the reference -- and a
+ * per-quantizer port -- spends ~15 tiny ATen launches per quantizer here, which dominates a streaming calibration).
+ *   symmetric: scale = max(max(-min(min,0), max(max,0)) * 2 / (qmax - qmin), 1e-6), zero_point = 0
+ *   affine:    scale = max((max(max,0) - min(min,0)) / (qmax - qmin), 1e-6), zero_point = round(-min(min,0) / scale)
+ * with IEEE fp32 operations in that order (bit-identical to the torch statement).  `device_table`: caller-owned scratch
+ * of count * 64 bytes.  Outputs hold `channels` floats each. */
+typedef struct sb200_minmax_qparams_desc {
+  const uint32_t* state;
+  float* out_min;
+  float* out_max;
+  float* out_scale;
+  float* out_zero_point;
+  int64_t channels;
+  int qmin, qmax, symmetric;
+} sb200_minmax_qparams_desc;
+int sb200_minmax_qparams_multi(const sb200_minmax_qparams_desc* descs, int count, void* device_table,
+                               size_t table_bytes, void* stream);
+
 /* KL-histogram (observers/kl_histogram.py:47-50 -> torch.histc on CPU).  counts[bins] (int64) is
  * accumulated in place.  `range` = device {lo, hi}.  Bin rule = ATen's CPU histc
  * (HistogramKernel.cpp, linear interpolation): pos = (int64)(((x - lo) * bins) / (hi - lo)) in
@@ -302,6 +321,21 @@ int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, co
                           const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
                           int group_size, const sb200_gptq4_options* options, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Up to 4 independent decode-sized linears (1 <= M <= 32 tokens, the same M for all) in ONE launch -- q / k / v or
+ * gate / up of a decoder layer.  A decode GEMV lives for a handful of DRAM latencies; launching them back to back leaves
+ * HBM idle between kernels.  Same contract per problem as sb200_gptq4_matmul (out pre-initialised, accumulated in place);
+ * requires N % 4 == 0 and a 16-byte aligned qweight. */
+typedef struct sb200_gptq4_problem {
+  const float* x;          /* [M, k] fp32 */
+  const int32_t* qweight;  /* [qweight_rows, n] */
+  float* out;              /* [M, n] fp32, accumulated in place */
+  const float* scales;     /* [n, G] */
+  const float* zeros;      /* [n, G] */
+  int64_t k, n, qweight_rows;
+  int group_size;          /* 0 = k */
+} sb200_gptq4_problem;
+int sb200_gptq4_matmul_batch(const sb200_gptq4_problem* problems, int count, int64_t m, void* stream);
+
 /* fp16 activations in, fp16 result out, WITHOUT the per-call casts of QuantLinear.forward (utils/quant.py:262-278 casts
  * x / scales / zeros / bias to fp32, materialises y = bias, and casts the result back):
  *   out_f16[m, n] = fp16( bias[n] + sum_k (scales * q - zeros) * x_f16[m, k] )          (overwrites out_f16)

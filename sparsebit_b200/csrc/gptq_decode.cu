@@ -45,20 +45,48 @@ __device__ __forceinline__ void hmma_16816(float (&d)[4], const uint32_t (&a)[4]
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Several independent linears that share M (q / k / v or gate / up of one decoder layer: same input, different weights)
+// run as ONE launch: a decode-sized GEMV lives for a few microseconds, i.e. a handful of DRAM latencies, so launching
+// them back to back leaves the memory system idle between kernels.  Passed by value (__grid_constant__).
+struct DecProblem {
+  const float* x;
+  const uint32_t* qw;
+  float* out;
+  const float* scales;
+  const float* zeros;
+  int K, N, KW, G, group_size;
+  int colblock_begin;  // first blockIdx.x of this problem
+};
+constexpr int kDecMaxProblems = 4;
+struct DecBatch {
+  DecProblem p[kDecMaxProblems];
+  int count;
+};
+
 // NB = number of 8-token blocks (tokens handled per pass = 8 * NB).  Dynamic shared memory:
 //   xh[8 NB][stride], xl[8 NB][stride] halves (stride = slice_k + 32: token rows start 64 bytes apart modulo 128, so the
 //   8 lanes of an LDS.128 phase hit distinct banks), xsum[8 NB][blocks_per_slice] floats, escale[8 NB] floats.
 template <int NB>
-__global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* __restrict__ x, const uint32_t* __restrict__ qw,
-                                                                 float* __restrict__ out, const float* __restrict__ scales,
-                                                                 const float* __restrict__ zeros, int M, int K, int N, int KW,
-                                                                 int G, int group_size, int blocks_per_slice) {
+__global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_constant__ DecBatch batch, int M,
+                                                                 int blocks_per_slice) {
   extern __shared__ __align__(16) unsigned char dsm[];
   constexpr int MT = 8 * NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, c = lane & 3;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < kDecMaxProblems; ++i)
+    if (i < batch.count && (int)blockIdx.x >= batch.p[i].colblock_begin) pi = i;
+  const float* __restrict__ x = batch.p[pi].x;
+  const uint32_t* __restrict__ qw = batch.p[pi].qw;
+  float* __restrict__ out = batch.p[pi].out;
+  const float* __restrict__ scales = batch.p[pi].scales;
+  const float* __restrict__ zeros = batch.p[pi].zeros;
+  const int K = batch.p[pi].K, N = batch.p[pi].N, KW = batch.p[pi].KW, G = batch.p[pi].G, group_size = batch.p[pi].group_size;
+  const int bx = (int)blockIdx.x - batch.p[pi].colblock_begin;
   const int nblk = (K + kDecBlockK - 1) / kDecBlockK;
   const int b0 = blockIdx.y * blocks_per_slice;
+  if (b0 >= nblk) return;  // a problem with a shorter K than the longest one of the batch
   const int nb = min(b0 + blocks_per_slice, nblk) - b0;
   const int slice_k = blocks_per_slice * kDecBlockK;
   const int stride = slice_k + 32;  // halves
@@ -68,7 +96,7 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* 
   float* escale = xsum + MT * blocks_per_slice;
   __shared__ int s_need_lo;
   __shared__ unsigned int s_amax[32];
-  const int nbase = blockIdx.x * kDecCols + warp * 32 + 4 * g;  // this lane's four features nbase .. nbase + 3
+  const int nbase = bx * kDecCols + warp * 32 + 4 * g;  // this lane's four features nbase .. nbase + 3
   const bool col_ok = nbase < N;                                  // N % 4 == 0: all four or none
   uint32_t bias;
   asm volatile("mov.b32 %0, 0x64006400;" : "=r"(bias));  // half2(1024, 1024), opaque to constant propagation
@@ -97,33 +125,37 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* 
     // ---- stage the activations of this K slice (work items = (token, 128-K block) pairs spread over the warps):
     // per-token power-of-two scale, fp16 hi / lo planes, 8-K permutation, per-block row sums
     const int pairs = tokens * blocks_per_slice;
-    for (int p = warp; p < pairs; p += kDecThreads / 32) {
+    float cache[4];  // the values of this warp's first (token, block) pair: read from global memory once
+    for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it) {
       const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
       const float* xr = x + (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       float amax = 0.f;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int kk = r * 32 + lane;
-        if (blk < nb && (b0 + blk) * kDecBlockK + kk < K) amax = fmaxf(amax, fabsf(__ldg(xr + kk)));
+        const float v = (blk < nb && (b0 + blk) * kDecBlockK + kk < K) ? __ldg(xr + kk) : 0.f;
+        if (it == 0) cache[r] = v;
+        amax = fmaxf(amax, fabsf(v));
       }
       amax = warp_max(amax);
       if (lane == 0 && amax < __int_as_float(0x7f800000)) atomicMax(&s_amax[t], __float_as_uint(amax));  // non-negative: bit order == value order
     }
     __syncthreads();
-    for (int p = warp; p < pairs; p += kDecThreads / 32) {
+    for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it) {
       const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
       const float* xr = x + (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
-      const float amax = __uint_as_float(s_amax[t]);
-      const int e = amax > 0.f ? ilogbf(amax) - 14 : 0;  // scaled slice max in [2^14, 2^15)
-      const float down = ldexpf(1.f, -e);
-      if (lane == 0 && blk == 0) escale[t] = ldexpf(1.f, e);
+      const uint32_t abits = s_amax[t];
+      // 2^-e with e = floor(log2(amax)) - 14, straight from the exponent field: scaled slice max in [2^14, 2^15)
+      const int ex = abits ? (int)(abits >> 23) - 127 - 14 : 0;
+      const float down = __uint_as_float((uint32_t)(127 - max(-126, min(127, ex))) << 23);
+      if (lane == 0 && blk == 0) escale[t] = __uint_as_float((uint32_t)(127 + max(-126, min(127, ex))) << 23);
       float s = 0.f;
       bool any_lo = false;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int kk = r * 32 + lane;
         const bool ok = blk < nb && ((b0 + blk) * kDecBlockK + kk < K);
-        const float v = ok ? __ldg(xr + kk) * down : 0.f;
+        const float v = (it == 0 ? cache[r] : (ok ? __ldg(xr + kk) : 0.f)) * down;
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));
         any_lo |= (__half_as_ushort(lo) & 0x7FFFu) != 0;
@@ -148,6 +180,14 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* 
         for (int j = 0; j < 4; ++j) acc[T][q][j] = 0.f;
 
     auto compute_group = [&](int bl, const uint4 (&w)[4]) {
+      // the group's scale / zero of this lane's four features, requested before the MMA chain that hides their latency
+      const int grp = ((b0 + bl) * kDecBlockK) / group_size;
+      float sc[4], zr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sc[i] = col_ok ? __ldg(scales + (size_t)(nbase + i) * G + grp) : 0.f;
+        zr[i] = col_ok ? __ldg(zeros + (size_t)(nbase + i) * G + grp) : 0.f;
+      }
       float d[2][NB][4];
 #pragma unroll
       for (int T = 0; T < 2; ++T)
@@ -195,12 +235,9 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* 
         }
       }
       // group epilogue: acc += scale * D - zeros * sum_k x   (rows: slot g -> feature 2T, slot g + 8 -> feature 2T + 1)
-      const int grp = ((b0 + bl) * kDecBlockK) / group_size;
 #pragma unroll
       for (int T = 0; T < 2; ++T) {
-        const int nA = nbase + 2 * T;
-        const float sA = col_ok ? __ldg(scales + (size_t)nA * G + grp) : 0.f, zA = col_ok ? __ldg(zeros + (size_t)nA * G + grp) : 0.f;
-        const float sB = col_ok ? __ldg(scales + (size_t)(nA + 1) * G + grp) : 0.f, zB = col_ok ? __ldg(zeros + (size_t)(nA + 1) * G + grp) : 0.f;
+        const float sA = sc[2 * T], zA = zr[2 * T], sB = sc[2 * T + 1], zB = zr[2 * T + 1];
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
           const float xs0 = xsum[(q * 8 + 2 * c) * blocks_per_slice + bl], xs1 = xsum[(q * 8 + 2 * c + 1) * blocks_per_slice + bl];
@@ -236,27 +273,33 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const float* 
 
 bool gptq4_decode_supported(const int32_t* qweight, long long N) { return (N % 4 == 0) && aligned16(qweight); }
 
-int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
-                 long long K, long long N, long long KW, int group_size, cudaStream_t st) {
-  const int G = (int)((K + group_size - 1) / group_size);
-  const int nblk = (int)((K + kDecBlockK - 1) / kDecBlockK);
-  const int colblocks = (int)((N + kDecCols - 1) / kDecCols);
+// `count` problems sharing M in one launch (count == 1: the plain entry point)
+int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStream_t st) {
+  DecBatch batch;
+  batch.count = count;
+  int colblocks = 0, nblk_max = 0;
+  for (int i = 0; i < count; ++i) {
+    batch.p[i] = probs[i];
+    batch.p[i].colblock_begin = colblocks;
+    colblocks += (probs[i].N + kDecCols - 1) / kDecCols;
+    const int nblk = (probs[i].K + kDecBlockK - 1) / kDecBlockK;
+    nblk_max = nblk > nblk_max ? nblk : nblk_max;
+  }
+  for (int i = count; i < kDecMaxProblems; ++i) batch.p[i] = batch.p[0];
   const int nbk = M <= 8 ? 1 : (M <= 16 ? 2 : 4);
   // K slices: ~5 CTAs per SM (what the register file holds: 4 warps x 96 registers), each streaming as long a K
   // range as that allows, bounded by the activation slice held in shared memory
   int want = (sm_count() * 5 + colblocks - 1) / colblocks;
   if (want < 1) want = 1;
-  if (want > nblk) want = nblk;
-  int S = (nblk + want - 1) / want;
+  if (want > nblk_max) want = nblk_max;
+  int S = (nblk_max + want - 1) / want;
   const int smax = nbk == 1 ? 8 : (nbk == 2 ? 4 : 2);
   if (S > smax) S = smax;
-  const int slices = (nblk + S - 1) / S;
+  const int slices = (nblk_max + S - 1) / S;
   const dim3 grid((unsigned)colblocks, (unsigned)slices);
-  const uint32_t* qw = reinterpret_cast<const uint32_t*>(qweight);
   const int mt = 8 * nbk;
   const size_t smem = (size_t)2 * mt * (S * kDecBlockK + 32) * sizeof(__half) + (size_t)mt * S * sizeof(float) + (size_t)mt * sizeof(float);
-#define SB_GO(NB_) \
-  gptq4_decode_kernel<NB_><<<grid, kDecThreads, smem, st>>>(x, qw, out, scales, zeros, (int)M, (int)K, (int)N, (int)KW, G, group_size, S)
+#define SB_GO(NB_) gptq4_decode_kernel<NB_><<<grid, kDecThreads, smem, st>>>(batch, (int)M, S)
   if (nbk == 1) SB_GO(1);
   else if (nbk == 2) SB_GO(2);
   else SB_GO(4);
@@ -265,4 +308,51 @@ int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float
   return SB200_OK;
 }
 
+int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
+                 long long K, long long N, long long KW, int group_size, cudaStream_t st) {
+  DecProblem p;
+  p.x = x;
+  p.qw = reinterpret_cast<const uint32_t*>(qweight);
+  p.out = out;
+  p.scales = scales;
+  p.zeros = zeros;
+  p.K = (int)K;
+  p.N = (int)N;
+  p.KW = (int)KW;
+  p.G = (int)((K + group_size - 1) / group_size);
+  p.group_size = group_size;
+  p.colblock_begin = 0;
+  return gptq4_decode_batch(&p, 1, M, st);
+}
+
 }  // namespace sb200
+
+using namespace sb200;
+
+extern "C" int sb200_gptq4_matmul_batch(const sb200_gptq4_problem* problems, int count, int64_t m, void* stream) {
+  SB_REQUIRE(problems && count >= 1 && count <= kDecMaxProblems, "sb200_gptq4_matmul_batch: 1 .. %d problems (got %d)", kDecMaxProblems, count);
+  SB_REQUIRE(m >= 1 && m <= 32, "sb200_gptq4_matmul_batch: decode-sized M only (1 .. 32, got %lld)", (long long)m);
+  DecProblem p[kDecMaxProblems];
+  for (int i = 0; i < count; ++i) {
+    const sb200_gptq4_problem& q = problems[i];
+    SB_REQUIRE(q.x && q.qweight && q.out && q.scales && q.zeros, "sb200_gptq4_matmul_batch: null pointer in problem %d", i);
+    SB_REQUIRE(q.k > 0 && q.n > 0 && q.k < (1LL << 31) && q.n < (1LL << 31), "sb200_gptq4_matmul_batch: bad shape in problem %d", i);
+    SB_REQUIRE(q.qweight_rows >= (q.k + 7) / 8, "sb200_gptq4_matmul_batch: qweight of problem %d has too few rows", i);
+    SB_REQUIRE(q.group_size == 0 || (q.group_size > 0 && q.group_size % 128 == 0),
+               "only group_size divisible by 128 is supported in 4-bit quantization (got %d)", q.group_size);
+    SB_REQUIRE(gptq4_decode_supported(q.qweight, q.n), "sb200_gptq4_matmul_batch: problem %d needs N %% 4 == 0 and a 16-byte aligned qweight", i);
+    const int gs = q.group_size ? q.group_size : (int)q.k;
+    p[i].x = q.x;
+    p[i].qw = reinterpret_cast<const uint32_t*>(q.qweight);
+    p[i].out = q.out;
+    p[i].scales = q.scales;
+    p[i].zeros = q.zeros;
+    p[i].K = (int)q.k;
+    p[i].N = (int)q.n;
+    p[i].KW = (int)q.qweight_rows;
+    p[i].G = (int)((q.k + gs - 1) / gs);
+    p[i].group_size = gs;
+    p[i].colblock_begin = 0;
+  }
+  return gptq4_decode_batch(p, count, m, (cudaStream_t)stream);
+}

@@ -29,7 +29,7 @@
 //   warp 1      MMA issuer (elect.sync lane), tcgen05.commit -> stage empty / chunk complete
 //   warp 2      TMEM allocator (512 columns: 256 accumulator + 3 stages x (32 hi + 32 lo) operand columns)
 //   warps 4-11  epilogue: each thread = one feature row (TMEM lane) x 128 tokens, fp32 register accumulators
-//   warps 12-19 unpack (two 4-warp sets alternating stages): packed words -> (q - zero) half2 integers ->
+//   warps 12-19 unpack (two 4-warp sets, each on one half of every stage's 64 K): packed words -> (q - zero) integers ->
 //               scaled hi / lo planes -> tcgen05.st.x8 into the stage's operand columns
 // Zero points.  GPTQ checkpoints store zeros = zero * scale with an integer zero (utils/quant.py:188); the prepare
 // kernel verifies that on the device.  If it does not hold, the MMA runs on q alone and the epilogue subtracts
@@ -53,7 +53,7 @@ constexpr int kGroup128 = 128;
 
 struct TsSmem {
   uint64_t full[kTsStages];   // TMA data of the stage landed
-  uint64_t ready[kTsStages];  // the stage's weight planes are in TMEM (4 warp arrivals)
+  uint64_t ready[kTsStages];  // the stage's weight planes are in TMEM (8 warp arrivals)
   uint64_t empty[kTsStages];  // the MMAs reading the stage completed (tcgen05.commit)
   uint64_t acc_full;          // a chunk's MMAs completed
   uint64_t acc_empty;         // the 8 epilogue warps drained the accumulator
@@ -143,7 +143,7 @@ gptq4_ts_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kTsStages; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->ready[s], 4);
+      mbar_init(&sm->ready[s], 8);  // one arrival per unpack warp (both sets work on every stage)
       mbar_init(&sm->empty[s], 1);
     }
     mbar_init(&sm->acc_full, 1);
@@ -237,25 +237,27 @@ gptq4_ts_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     asm volatile("mov.b32 %0, 0x64006400;" : "=r"(bias));  // half2(1024, 1024); opaque to constant propagation
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCols;
     const __half2 k16 = __float2half2_rn(0.0625f);
-    uint32_t it0 = 0;  // stage counter of the tile's first K block; this set takes the stages with (it % 2) == uset
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it0 += (uint32_t)num_kb) {
+    // Both 4-warp sets work on EVERY stage, each on one half of its 64 K (set 0: packed rows 0-3 = MMA K steps 0, 1;
+    // set 1: rows 4-7 = K steps 2, 3).  (Alternating whole stages between the sets would make each set see only every
+    // other phase of full[s] -- 3 stages, 2 sets -- and a parity wait cannot tell "my phase completed" from "the
+    // barrier is still a phase behind me": with tiny MMAs a set that ran ahead of the TMA frontier unpacked stale words.)
+    uint32_t it = 0;  // stage counter, continues across tiles
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n = (tile / tiles_m) * kWRows + t;
       const bool live = n < N;
-      const int kb0 = (int)((it0 + uset) & 1u);  // first K block of this tile that belongs to this set
-      // quantisation group of the stage, advanced incrementally; its parameters are fetched one iteration ahead
-      int gq_next = (kb0 * kTsBK) / group_size;
-      long long koff_next = (long long)kb0 * kTsBK;
+      // quantisation group of the stage, advanced incrementally; its parameters are fetched one stage ahead
+      int gq_next = 0;
+      long long koff_next = 0;
       auto fetch = [&](int kb) -> uint2 {
         if (!live || kb >= num_kb) return make_uint2(0u, 0u);
         return __ldg(sz + (size_t)n * Gq + gq_next);
       };
-      uint2 p_cur = fetch(kb0);
-      for (int kb = kb0; kb < num_kb; kb += 2) {
-        const uint32_t it = it0 + (uint32_t)kb;
+      uint2 p_cur = fetch(0);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const uint32_t s = it % kTsStages, ph = (it / kTsStages) & 1u;
-        koff_next += 2 * kTsBK;
+        koff_next += kTsBK;
         while (koff_next >= (long long)(gq_next + 1) * group_size) ++gq_next;
-        const uint2 p_next = fetch(kb + 2);
+        const uint2 p_next = fetch(kb + 1);
         // scale planes and zero point of this stage's group
         const __half2 sh2 = __half2half2(__ushort_as_half((unsigned short)(p_cur.x & 0xFFFFu)));
         const __half2 sl2 = __half2half2(__ushort_as_half((unsigned short)(p_cur.x >> 16)));
@@ -265,16 +267,17 @@ gptq4_ts_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         p_cur = p_next;
         mbar_wait_relaxed(&sm->full[s], ph, 0);
         const uint32_t* bq = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * kTsStageBytes + 2 * kXBytes);
-        uint32_t w[kTsBK / 8];
+        uint32_t w[kTsBK / 16];
 #pragma unroll
-        for (int r = 0; r < kTsBK / 8; ++r) w[r] = bq[r * kWRows + t];
+        for (int r = 0; r < kTsBK / 16; ++r) w[r] = bq[(uset * (kTsBK / 16) + r) * kWRows + t];
         const uint32_t abase = lane_base + s * kAStageCols;
 #pragma unroll
-        for (int p = 0; p < kTsBK / 16; ++p) {  // two packed words = 16 K = one MMA K step = 8 TMEM columns per plane
+        for (int pp = 0; pp < kTsBK / 32; ++pp) {  // two packed words = 16 K = one MMA K step = 8 TMEM columns per plane
+          const int p = (int)uset * (kTsBK / 32) + pp;
           uint32_t H[8], L[8];
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const uint32_t lo32 = w[2 * p + i], hi32 = lo32 >> 8;
+            const uint32_t lo32 = w[2 * pp + i], hi32 = lo32 >> 8;
             // 0x6400 | q = fp16(1024 + q);  0x6400 | (q << 4) = fp16(1024 + 16 q)
             const __half2 v0 = u2h2(and_or<0x000F000Fu>(lo32, bias));  // k = 8r + (0, 4)
             const __half2 v1 = u2h2(and_or<0x00F000F0u>(lo32, bias));  // k = 8r + (1, 5), times 16

@@ -115,6 +115,43 @@ __global__ void __launch_bounds__(256) mask_rows_gt_kernel(const float* __restri
   }
 }
 
+// MinMax observers of a whole model: running min/max states -> (min, max, scale, zero_point) in ONE launch
+// (observers/minmax.py:14-25 + Observer.calc_qparams_with_minmax, observers/base.py:63-79, which the reference runs as
+// ~15 tiny ATen ops per quantizer).  One CTA per quantizer; IEEE op order of the Python statement, NaN propagating like
+// torch.minimum / torch.maximum.
+struct QparamEntry {  // device-side descriptor, 64 bytes
+  const uint32_t* state;  // {enc(min), enc(max)} per channel
+  float* out_min;
+  float* out_max;
+  float* out_scale;
+  float* out_zp;
+  long long channels;
+  float span;  // qmax - qmin
+  int symmetric;
+  long long pad;
+};
+static_assert(sizeof(QparamEntry) == 64, "QparamEntry layout");
+
+__global__ void __launch_bounds__(128) minmax_qparams_kernel(const QparamEntry* __restrict__ table) {
+  const QparamEntry e = table[blockIdx.x];
+  for (long long c = threadIdx.x; c < e.channels; c += blockDim.x) {
+    const float mn = dec_f32(e.state[2 * c]), mx = dec_f32(e.state[2 * c + 1]);
+    const float min_neg = fmin_nan(mn, 0.f), max_pos = fmax_nan(mx, 0.f);
+    float scale, zp;
+    if (e.symmetric) {
+      scale = fmax_nan(__fdiv_rn(__fmul_rn(fmax_nan(-min_neg, max_pos), 2.f), e.span), 1e-6f);
+      zp = 0.f;
+    } else {
+      scale = fmax_nan(__fdiv_rn(__fsub_rn(max_pos, min_neg), e.span), 1e-6f);
+      zp = rintf(__fdiv_rn(-min_neg, scale));
+    }
+    e.out_min[c] = mn;
+    e.out_max[c] = mx;
+    e.out_scale[c] = scale;
+    e.out_zp[c] = zp;
+  }
+}
+
 }  // namespace sb200
 
 using namespace sb200;
@@ -149,6 +186,31 @@ int sb200_qdq_multi_plan(const sb200_qdq_tensor_desc* descs, int count, void* de
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
   delete[] host;
   SB_CUDA(e);
+  return SB200_OK;
+}
+
+int sb200_minmax_qparams_multi(const sb200_minmax_qparams_desc* descs, int count, void* device_table, size_t table_bytes,
+                               void* stream) {
+  SB_REQUIRE(descs && device_table, "sb200_minmax_qparams_multi: null pointer argument");
+  SB_REQUIRE(count > 0 && count <= 65535, "sb200_minmax_qparams_multi: count must be in [1, 65535] (got %d)", count);
+  SB_REQUIRE(table_bytes >= (size_t)count * sizeof(QparamEntry), "sb200_minmax_qparams_multi: table too small");
+  QparamEntry* host = new QparamEntry[count];
+  for (int i = 0; i < count; ++i) {
+    const sb200_minmax_qparams_desc& d = descs[i];
+    if (!d.state || !d.out_min || !d.out_max || !d.out_scale || !d.out_zero_point || d.channels <= 0 || d.qmin >= d.qmax) {
+      delete[] host;
+      set_error("sb200_minmax_qparams_multi: bad descriptor %d (null pointer, no channels or qmin >= qmax)", i);
+      return SB200_E_INVALID;
+    }
+    host[i] = QparamEntry{d.state, d.out_min, d.out_max, d.out_scale, d.out_zero_point, (long long)d.channels,
+                          (float)(d.qmax - d.qmin), d.symmetric ? 1 : 0, 0};
+  }
+  cudaError_t e = cudaMemcpyAsync(device_table, host, (size_t)count * sizeof(QparamEntry), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);  // the staging copy is freed right below
+  delete[] host;
+  SB_CUDA(e);
+  minmax_qparams_kernel<<<(unsigned)count, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const QparamEntry*>(device_table));
+  SB_LAUNCHED();
   return SB200_OK;
 }
 

@@ -11,6 +11,7 @@ generator (``calc_qparams_steps``) that *yields* what it needs merged:
     Sync.sum(tensors)   int64 histograms / counts, fp64 moment and squared-error sums: one SUM all-reduce
                         (everything travels as fp64; counts are exact below 2^53)
     Sync.gather(tensor) per-sample statistics whose order matters (MovingAverage): one all-gather
+    Sync.qparams(...)   (no communication) min/max state -> qparams, batched into one launch for the whole model
 
 ``drive(gen)`` runs ONE observer and performs each request on its own.  ``drive_all(gens)`` advances
 EVERY quantizer of a model in lockstep and packs the requests of a round into ONE MAX, ONE SUM (and one
@@ -72,6 +73,15 @@ class Sync:
     @classmethod
     def gather(cls, tensor, local=False):
         return cls("gather", [tensor], local)
+
+    @classmethod
+    def qparams(cls, state, qmin, qmax, symmetric):
+        """Not a collective: (min, max, scale, zero_point) of a running min/max state.  Batched by the drivers so that
+        all MinMax quantizers of a model finish in ONE kernel launch (sb200_minmax_qparams_multi) instead of ~15 tiny
+        ATen launches each."""
+        req = cls("qparams", [state], True)
+        req.result = (int(qmin), int(qmax), bool(symmetric))
+        return req
 
 
 # ----------------------------------------------------------------------------- packing helpers
@@ -158,6 +168,12 @@ def _serve(requests):
     for r in requests:
         if r is not None and r.kind == "gather" and r.result is None:
             r.result = [r.tensors[0]]
+    qp = [r for r in requests if r is not None and r.kind == "qparams"]
+    if qp:
+        from . import ops
+
+        for r, out in zip(qp, ops.minmax_qparams_multi([(r.tensors[0],) + r.result for r in qp])):
+            r.result = out
 
 
 def drive(gen):

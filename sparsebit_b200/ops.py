@@ -279,6 +279,36 @@ def minmax_read(state):
     return mn, mx
 
 
+class _QparamsDesc(ctypes.Structure):  # include/sparsebit_b200.h sb200_minmax_qparams_desc
+    _fields_ = [("state", ctypes.c_void_p), ("out_min", ctypes.c_void_p), ("out_max", ctypes.c_void_p), ("out_scale", ctypes.c_void_p),
+                ("out_zero_point", ctypes.c_void_p), ("channels", ctypes.c_int64), ("qmin", ctypes.c_int), ("qmax", ctypes.c_int),
+                ("symmetric", ctypes.c_int)]
+
+
+def minmax_qparams_multi(requests):
+    """``requests``: [(state int32[2C], qmin, qmax, symmetric)] -> [(min, max, scale, zero_point)] float32[C] views of one
+    buffer, computed by ONE launch (sb200_minmax_qparams_multi)."""
+    lib = _lib.load()
+    if not requests:
+        return []
+    dev = requests[0][0].device
+    chans = [r[0].numel() // 2 for r in requests]
+    total = sum(chans)
+    flat = torch.empty(4, total, dtype=torch.float32, device=dev)
+    table = torch.empty(64 * len(requests), dtype=torch.uint8, device=dev)
+    descs, outs, off = [], [], 0
+    base, plane = flat.data_ptr(), total * 4
+    for (state, qmin, qmax, sym), c in zip(requests, chans):
+        p = base + off * 4
+        descs.append(_QparamsDesc(state.data_ptr(), p, p + plane, p + 2 * plane, p + 3 * plane, c, int(qmin), int(qmax), int(bool(sym))))
+        outs.append(tuple(flat[k, off:off + c] for k in range(4)))
+        off += c
+    arr = (_QparamsDesc * len(descs))(*descs)
+    with torch.cuda.device(dev):
+        check(lib.sb200_minmax_qparams_multi(arr, len(descs), table.data_ptr(), table.numel(), torch.cuda.current_stream(dev).cuda_stream))
+    return outs
+
+
 # ----------------------------------------------------------------------------- histogram / MSE
 def hist_update(x, range_lo_hi, counts):
     """counts (int64[bins]) += histc(x, bins, lo, hi); ``range_lo_hi``: device float32[2]."""
@@ -458,6 +488,36 @@ def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0, impl=None, chunk_
                                             zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size), ctypes.byref(opts),
                                             ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x)))
     return out
+
+
+class _Gptq4Problem(ctypes.Structure):  # include/sparsebit_b200.h sb200_gptq4_problem
+    _fields_ = [("x", ctypes.c_void_p), ("qweight", ctypes.c_void_p), ("out", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+                ("zeros", ctypes.c_void_p), ("k", ctypes.c_int64), ("n", ctypes.c_int64), ("qweight_rows", ctypes.c_int64),
+                ("group_size", ctypes.c_int)]
+
+
+def gptq4_matmul_batch(problems, group_size=0):
+    """Up to 4 decode-sized linears sharing M in ONE launch (q / k / v, gate / up): ``problems`` = [(x, qweight, out, scales,
+    zeros)], every ``out`` pre-initialised and accumulated in place (sb200_gptq4_matmul_batch)."""
+    lib = _lib.load()
+    m = None
+    arr = (_Gptq4Problem * len(problems))()
+    for i, (x, qw, out, sc, zr) in enumerate(problems):
+        _req(x, "inp1"), _req(out, "out"), _req(sc, "scales"), _req(zr, "zeros"), _req(qw, "inp2", torch.int32)
+        k = x.shape[-1]
+        mi = x.numel() // k
+        if m is None:
+            m = mi
+        elif mi != m:
+            raise SparsebitB200Error("gptq4_matmul_batch: all problems must have the same number of tokens")
+        if out.shape[-1] != qw.shape[1]:
+            raise SparsebitB200Error("output channel must be the same with input2 out_channel")
+        arr[i] = _Gptq4Problem(x.data_ptr(), qw.data_ptr(), out.data_ptr(), sc.data_ptr(), zr.data_ptr(), k, qw.shape[1], qw.shape[0],
+                               int(group_size))
+    dev = problems[0][0].device
+    with torch.cuda.device(dev):
+        check(lib.sb200_gptq4_matmul_batch(arr, len(problems), m, torch.cuda.current_stream(dev).cuda_stream))
+    return [p[2] for p in problems]
 
 
 def gptq4_linear_f16(x, qweight, scales, zeros, bias=None, group_size=0):

@@ -394,3 +394,86 @@ def test_tcgen05_numeric_scheme_meets_the_reference_tolerance():
             acc = (acc + scales[:, g][None, :] * part).astype(np.float32)
         got = (np.broadcast_to(bias, (9, n)) + np.ldexp(acc, e[:, None])).astype(np.float32)
         np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-5, err_msg=case)
+
+
+def test_qdq_onnx_export_emits_quantize_dequantize_linear(monkeypatch):
+    """QDQ-ONNX export (quant_model.py:217-260 -> quant_tensor.py:220-249): with ``export_onnx`` set, Quantizer.forward
+    must stay on the stock ATen fake-quantize ops so that the exporter emits QuantizeLinear / DequantizeLinear -- the
+    custom kernels are not involved.  (The ``onnx`` Python package is absent in this image; the TorchScript exporter
+    only needs it for a post-processing hook that is irrelevant here, so the hook is bypassed and the serialized graph
+    is inspected as bytes.)"""
+    import io
+    import warnings
+
+    from torch.onnx._internal.torchscript_exporter import onnx_proto_utils
+
+    monkeypatch.setattr(onnx_proto_utils, "_add_onnxscript_fn", lambda proto, custom_opsets: proto)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(8, 4)
+            self.aq = build_quantizer(sbcfg.quantizer_config("per-tensor-affine", 8, "feature"))
+            self.wq = build_quantizer(sbcfg.quantizer_config("per-channel-symmetric", 8, "weight"))
+
+        def forward(self, x):
+            return torch.nn.functional.linear(self.aq(x), self.wq(self.lin.weight), self.lin.bias)
+
+    m = M().cpu().eval()
+    for q, s, z in ((m.aq, torch.tensor([0.05]), torch.tensor([3.0])), (m.wq, torch.rand(4, 1) * 0.01 + 0.01, torch.zeros(4, 1))):
+        q.scale, q.zero_point = s, z
+        q.set_backend(Backend.ONNXRUNTIME)
+        q.enable_quant()
+        q.enable_export_onnx()
+    x = torch.randn(2, 8)
+    # the export branch equals the stock fake-quantize ops (no native library involved: this runs on the CPU)
+    torch.testing.assert_close(m.aq(x), torch.fake_quantize_per_tensor_affine(x, 0.05, 3, 0, 255))
+    buf = io.BytesIO()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.onnx.export(m, (x,), buf, opset_version=13, dynamo=False)
+    data = buf.getvalue()
+    assert data.count(b"QuantizeLinear") >= 4 and data.count(b"DequantizeLinear") >= 2  # one Q / DQ pair per quantizer
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/sparsebit"), reason="needs the reference checkout (build container only)")
+def test_install_under_reference_quantmodel_resnet18_graph_build():
+    """install() + the UNMODIFIED reference's QuantModel(torchvision resnet18): the fx graph build, operator
+    replacement and quantizer construction still work with the native observers / runner / fake_quant module rebound
+    (quant_model.py:185-189 imports the runner at call time)."""
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, "tests/golden")
+        import _ref_import as R
+        R.install_shims()
+        import torch, torchvision
+        import sparsebit_b200
+        sparsebit_b200.install()
+        from sparsebit.quantization import QuantModel
+        from sparsebit.quantization.quant_config import _C
+        cfg = _C.clone(); cfg.DEVICE = "cpu"
+        cfg.W.QSCHEME = "per-channel-symmetric"; cfg.W.QUANTIZER.BIT = 8
+        cfg.A.QSCHEME = "per-tensor-affine"; cfg.A.QUANTIZER.BIT = 8
+        qm = QuantModel(torchvision.models.resnet18(weights=None).eval(), cfg)
+        qm.prepare_calibration()
+        oprs = [m for m in qm.model.modules() if hasattr(m, "input_quantizer")]
+        assert len(oprs) >= 40, len(oprs)
+        assert type(qm.calibration_runner).__module__ == "sparsebit_b200.quantization.tools.calibration"
+        native = [m for m in oprs if type(m.input_quantizer.observer).__module__.startswith("sparsebit_b200.")]
+        assert len(native) == len(oprs)
+        # LSQ of the reference keeps working on native observers: its constructor hook makes them retain batches
+        cfg2 = _C.clone(); cfg2.DEVICE = "cpu"; cfg2.W.QSCHEME = "per-channel-symmetric"; cfg2.W.QUANTIZER.BIT = 4
+        cfg2.W.QUANTIZER.TYPE = "lsq"; cfg2.A.QSCHEME = "per-tensor-affine"; cfg2.A.QUANTIZER.BIT = 4; cfg2.A.QUANTIZER.TYPE = "lsq"
+        qm2 = QuantModel(torchvision.models.resnet18(weights=None).eval(), cfg2)
+        lsq = [m.weight_quantizer for m in qm2.model.modules() if getattr(m, "weight_quantizer", None) is not None]
+        assert lsq and all(q.observer.keep_data for q in lsq)
+        print("GRAPH_OK", len(oprs))
+    """)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip().splitlines()[-1].startswith("GRAPH_OK")
