@@ -129,6 +129,16 @@ int sb200_qdq_perchannel_bwd_ex(const float* x, const float* scale, const float*
                                 int rounding, int flags, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
+/* PACT (quantizers/pact.py:43-46) clamps the activation to the learnable [lower, alpha] in front of the fake-quant op and
+ * lets autograd differentiate the clamp.  The clamp does not change the forward value (the QDQ grid derived from
+ * [lower, alpha] clamps to the same points), so the native PACT quantizer skips that 8 B/elem pass and only needs the
+ * clamp's backward:   grad_x = grad_y * [lo <= x <= hi],  grad_hi = sum grad_y * [x > hi],  grad_lo = sum grad_y * [x < lo]
+ * (torch.clamp's convention).  lo / hi: device scalars.  grad_hi / grad_lo may be NULL.  Deterministic. */
+size_t sb200_clamp_bwd_workspace_bytes(int64_t n);
+int sb200_clamp_bwd(const float* x, const float* grad_y, const float* lo, const float* hi, float* grad_x,
+                    float* grad_hi, float* grad_lo, int64_t n, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* ---- (2) Observer calibration reductions -------------------------------------------------
  * MinMax (observers/minmax.py:14-25 -- torch.cat + min/max).  Streaming: the state is updated
  * in place per batch, nothing is cached or concatenated.  State layout: uint32[2*C], entry 2c =

@@ -110,6 +110,32 @@ def run(ms, with_reference=True, quiet=False):
                       "TFLOPs": 2.0 * m * k * n / t / 1e12, "weight_GBps": (wbytes + 2 * n * (k // 128) * 4) / t / 1e9})
                 totals[(m, "reference_cuda")] = totals.get((m, "reference_cuda"), 0.0) + t * cnt * LAYERS
             del ws
+    # decode with the same-input linears of a layer fused into one launch each: [q, k, v], o, [gate, up], down
+    for m in ms:
+        if m > 32:
+            continue
+        try:
+            sets = {name: make(k, n, max(2, min(8, (256 << 20) // (k * n // 2 * cnt) + 1)) * cnt) for name, k, n, cnt in SHAPES}
+            xq = torch.randn(m, 4096, device=dev).half().float()
+            xd = torch.randn(m, 11008, device=dev).half().float()
+            ys = {"qkvo": [torch.zeros(m, 4096, device=dev) for _ in range(4)], "gate_up": [torch.zeros(m, 11008, device=dev) for _ in range(2)],
+                  "down": [torch.zeros(m, 4096, device=dev)]}
+            rounds = min(len(sets["qkvo"]) // 4, len(sets["gate_up"]) // 2, len(sets["down"]))
+
+            def layer(i):
+                q4, gu, dn = sets["qkvo"][4 * i:4 * i + 4], sets["gate_up"][2 * i:2 * i + 2], sets["down"][i]
+                ops.gptq4_matmul_batch([(xq, w[0], y, w[1], w[2]) for w, y in zip(q4[:3], ys["qkvo"][:3])], 128)
+                ops.gptq4_matmul(xq, q4[3][0], ys["qkvo"][3], q4[3][1], q4[3][2], 128)
+                ops.gptq4_matmul_batch([(xq, w[0], y, w[1], w[2]) for w, y in zip(gu, ys["gate_up"])], 128)
+                ops.gptq4_matmul(xd, dn[0], ys["down"][0], dn[1], dn[2], 128)
+
+            t = timeit(lambda i: layer(i % rounds), 60, rounds)
+            emit({"shape": "layer(qkv|o|gate_up|down)", "M": m, "impl": "ours_fused_launches", "us": t * 1e6,
+                  "weight_GBps": (6_476_005_376 / 32 / 2 + 2 * 4 * 6_476_005_376 / 32 / 128) / t / 1e9})
+            totals[(m, "ours_fused_launches")] = t * LAYERS
+            del sets
+        except Exception as e:  # keep the per-linear numbers
+            emit({"M": m, "impl": "ours_fused_launches", "error": repr(e)[:160]})
     return totals
 
 

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "sb200_qdq_pertensor_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "sb200_qdq_perchannel_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "sb200_qdq_perchannel_bwd_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
+    "sb200_clamp_bwd_workspace_bytes": (c_sz, [c_i64]),
+    "sb200_clamp_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "sb200_minmax_init": (c_int, [c_vp, c_i64, c_vp]),
     "sb200_observe_minmax": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "sb200_observe_minmax_perchannel": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),

@@ -65,7 +65,8 @@ struct DecBatch {
 
 // NB = number of 8-token blocks (tokens handled per pass = 8 * NB).  Dynamic shared memory:
 //   xh[8 NB][stride], xl[8 NB][stride] halves (stride = slice_k + 32: token rows start 64 bytes apart modulo 128, so the
-//   8 lanes of an LDS.128 phase hit distinct banks), xsum[8 NB][blocks_per_slice] floats, escale[8 NB] floats.
+//   8 lanes of an LDS.128 phase hit distinct banks), xsum[8 NB][blocks_per_slice] floats, escale[8 NB] floats,
+//   scale / zeros [blocks_per_slice][128] floats each.
 template <int NB>
 __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_constant__ DecBatch batch, int M,
                                                                  int blocks_per_slice) {
@@ -94,6 +95,8 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
   __half* xl = xh + MT * stride;
   float* xsum = reinterpret_cast<float*>(xl + MT * stride);
   float* escale = xsum + MT * blocks_per_slice;
+  float* s_sc = escale + MT;                          // [blocks_per_slice][128] scale of (block, feature of this CTA)
+  float* s_zr = s_sc + blocks_per_slice * kDecCols;   // [blocks_per_slice][128] zeros
   __shared__ int s_need_lo;
   __shared__ unsigned int s_amax[32];
   const int nbase = bx * kDecCols + warp * 32 + 4 * g;  // this lane's four features nbase .. nbase + 3
@@ -110,6 +113,19 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       w[ch] = (col_ok && row < KW) ? __ldcs(reinterpret_cast<const uint4*>(qw + (size_t)row * N + nbase)) : make_uint4(0u, 0u, 0u, 0u);
     }
   };
+
+  // scales / zeros of this CTA's 128 features for every 128-K block of its slice: thread = feature, so the table is
+  // read with one request per (feature, block) instead of one per (lane, feature, block) -- the [N, G] checkpoint layout
+  // puts consecutive features G floats apart, and fetching them lane by lane inside the group loop cost 4x the sectors
+  // of the packed weights themselves
+  {
+    const int n = bx * kDecCols + tid;
+    for (int bl = 0; bl < nb; ++bl) {
+      const int grp = ((b0 + bl) * kDecBlockK) / group_size;
+      s_sc[bl * kDecCols + tid] = n < N ? __ldg(scales + (size_t)n * G + grp) : 0.f;
+      s_zr[bl * kDecCols + tid] = n < N ? __ldg(zeros + (size_t)n * G + grp) : 0.f;
+    }
+  }
 
   for (int m0 = 0; m0 < M; m0 += MT) {
     // The kernel lives for a few microseconds, i.e. a handful of DRAM latencies: the packed weights of the first two
@@ -180,14 +196,6 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
         for (int j = 0; j < 4; ++j) acc[T][q][j] = 0.f;
 
     auto compute_group = [&](int bl, const uint4 (&w)[4]) {
-      // the group's scale / zero of this lane's four features, requested before the MMA chain that hides their latency
-      const int grp = ((b0 + bl) * kDecBlockK) / group_size;
-      float sc[4], zr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sc[i] = col_ok ? __ldg(scales + (size_t)(nbase + i) * G + grp) : 0.f;
-        zr[i] = col_ok ? __ldg(zeros + (size_t)(nbase + i) * G + grp) : 0.f;
-      }
       float d[2][NB][4];
 #pragma unroll
       for (int T = 0; T < 2; ++T)
@@ -237,7 +245,8 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       // group epilogue: acc += scale * D - zeros * sum_k x   (rows: slot g -> feature 2T, slot g + 8 -> feature 2T + 1)
 #pragma unroll
       for (int T = 0; T < 2; ++T) {
-        const float sA = sc[2 * T], zA = zr[2 * T], sB = sc[2 * T + 1], zB = zr[2 * T + 1];
+        const int f = bl * kDecCols + warp * 32 + 4 * g + 2 * T;  // lanes of one g read the same word: conflict-free
+        const float sA = s_sc[f], zA = s_zr[f], sB = s_sc[f + 1], zB = s_zr[f + 1];
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
           const float xs0 = xsum[(q * 8 + 2 * c) * blocks_per_slice + bl], xs1 = xsum[(q * 8 + 2 * c + 1) * blocks_per_slice + bl];
@@ -298,7 +307,8 @@ int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStre
   const int slices = (nblk_max + S - 1) / S;
   const dim3 grid((unsigned)colblocks, (unsigned)slices);
   const int mt = 8 * nbk;
-  const size_t smem = (size_t)2 * mt * (S * kDecBlockK + 32) * sizeof(__half) + (size_t)mt * S * sizeof(float) + (size_t)mt * sizeof(float);
+  const size_t smem = (size_t)2 * mt * (S * kDecBlockK + 32) * sizeof(__half) + (size_t)mt * S * sizeof(float) + (size_t)mt * sizeof(float) +
+                      (size_t)2 * S * kDecCols * sizeof(float);
 #define SB_GO(NB_) gptq4_decode_kernel<NB_><<<grid, kDecThreads, smem, st>>>(batch, (int)M, S)
   if (nbk == 1) SB_GO(1);
   else if (nbk == 2) SB_GO(2);

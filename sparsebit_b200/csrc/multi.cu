@@ -152,6 +152,60 @@ __global__ void __launch_bounds__(128) minmax_qparams_kernel(const QparamEntry* 
   }
 }
 
+// PACT (quantizers/pact.py:43-46): backward of clamp(x, lo, hi) with learnable bounds, the only thing the reference's
+// extra clamp pass in front of the fake-quant op contributes (the forward value is unchanged: the QDQ grid built from
+// [lo, hi] clamps to the same points).   gx = gy * [lo <= x <= hi];  g_hi = sum gy * [x > hi];  g_lo = sum gy * [x < lo]
+// (torch.clamp's gradient convention).  12 B/elem; per-CTA fp64 partials + a fixed-order finish => deterministic.
+__global__ void __launch_bounds__(256) clamp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                        const float* __restrict__ lo_p, const float* __restrict__ hi_p,
+                                                        float* __restrict__ gx, long long n, double2* __restrict__ partial) {
+  __shared__ double s_red[2][8];
+  const float lo = __ldg(lo_p), hi = __ldg(hi_p);
+  double d_hi = 0.0, d_lo = 0.0;
+  float a_hi = 0.f, a_lo = 0.f;
+  int k = 0;
+  auto one = [&](float xv, float g) -> float {
+    a_hi += xv > hi ? g : 0.f;
+    a_lo += xv < lo ? g : 0.f;
+    return (xv >= lo && xv <= hi) ? g : 0.f;
+  };
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx)) & 15u) == 0;
+  const long long nv = vec ? (n >> 2) : 0;
+  for (long long i = t0; i < nv; i += nt) {
+    const float4 xv = ld_stream4(reinterpret_cast<const float4*>(x) + i), g = ld_stream4(reinterpret_cast<const float4*>(gy) + i);
+    float4 o;
+    o.x = one(xv.x, g.x); o.y = one(xv.y, g.y); o.z = one(xv.z, g.z); o.w = one(xv.w, g.w);
+    st_stream4(reinterpret_cast<float4*>(gx) + i, o);
+    if (++k == 64) { d_hi += a_hi; d_lo += a_lo; a_hi = a_lo = 0.f; k = 0; }  // bound the fp32 accumulation length
+  }
+  for (long long i = (nv << 2) + t0; i < n; i += nt) gx[i] = one(__ldcs(x + i), __ldcs(gy + i));
+  d_hi += a_hi;
+  d_lo += a_lo;
+  d_hi = warp_sum(d_hi);
+  d_lo = warp_sum(d_lo);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_red[0][wid] = d_hi; s_red[1][wid] = d_lo; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double h = 0.0, l = 0.0;
+    for (int w = 0; w < 8; ++w) { h += s_red[0][w]; l += s_red[1][w]; }
+    partial[blockIdx.x] = make_double2(h, l);
+  }
+}
+__global__ void clamp_bwd_finish_kernel(const double2* __restrict__ partial, int n, float* __restrict__ g_hi, float* __restrict__ g_lo) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double h = 0.0, l = 0.0;
+    for (int i = 0; i < n; ++i) { h += partial[i].x; l += partial[i].y; }
+    if (g_hi) g_hi[0] = (float)h;
+    if (g_lo) g_lo[0] = (float)l;
+  }
+}
+static inline int clamp_bwd_ctas(long long n) {
+  long long c = (n / 4 + 255) / 256, cap = (long long)sm_count() * 4;
+  return (int)(c < 1 ? 1 : (c > cap ? cap : c));
+}
+
 }  // namespace sb200
 
 using namespace sb200;
@@ -210,6 +264,24 @@ int sb200_minmax_qparams_multi(const sb200_minmax_qparams_desc* descs, int count
   delete[] host;
   SB_CUDA(e);
   minmax_qparams_kernel<<<(unsigned)count, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const QparamEntry*>(device_table));
+  SB_LAUNCHED();
+  return SB200_OK;
+}
+
+size_t sb200_clamp_bwd_workspace_bytes(int64_t n) { return n > 0 ? (size_t)clamp_bwd_ctas(n) * sizeof(double2) : 0; }
+
+int sb200_clamp_bwd(const float* x, const float* grad_y, const float* lo, const float* hi, float* grad_x, float* grad_hi,
+                    float* grad_lo, int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
+  SB_REQUIRE(x && grad_y && lo && hi && grad_x, "sb200_clamp_bwd: null pointer argument");
+  SB_REQUIRE(n > 0, "sb200_clamp_bwd: Kernel Failure, Tensor is empty: data");
+  const int ctas = clamp_bwd_ctas(n);
+  if (!workspace || workspace_bytes < (size_t)ctas * sizeof(double2)) {
+    set_error("sb200_clamp_bwd: workspace too small");
+    return SB200_E_WORKSPACE;
+  }
+  clamp_bwd_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(x, grad_y, lo, hi, grad_x, n, (double2*)workspace);
+  SB_LAUNCHED();
+  clamp_bwd_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double2*)workspace, ctas, grad_hi, grad_lo);
   SB_LAUNCHED();
   return SB200_OK;
 }

@@ -78,6 +78,23 @@ def qdq_stats_pertensor(x, scale, zero_point, qmin, qmax, state, rounding=0, out
 
 
 # ----------------------------------------------------------------------------- STE backward
+def clamp_backward(x, grad_y, lo, hi):
+    """Backward of ``clamp(x, lo, hi)`` with tensor bounds: (gx, g_hi, g_lo) -- sb200_clamp_bwd (PACT)."""
+    lib = _lib.load()
+    _req(x, "data"), _req(grad_y, "grad"), _req(lo, "lower"), _req(hi, "alpha")
+    if grad_y.shape != x.shape:
+        raise SparsebitB200Error("grad_y must have the shape of data")
+    gx = torch.empty_like(x)
+    g_hi = torch.zeros(1, dtype=torch.float32, device=x.device)
+    g_lo = torch.zeros(1, dtype=torch.float32, device=x.device)
+    ws_bytes = int(lib.sb200_clamp_bwd_workspace_bytes(x.numel()))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sb200_clamp_bwd(x.data_ptr(), grad_y.data_ptr(), lo.data_ptr(), hi.data_ptr(), gx.data_ptr(), g_hi.data_ptr(),
+                                  g_lo.data_ptr(), x.numel(), ws.data_ptr(), ws_bytes, _stream(x)))
+    return gx, g_hi, g_lo
+
+
 BWD_GZP_CLOSED = 1  # include/sparsebit_b200.h SB200_BWD_GZP_CLOSED
 
 

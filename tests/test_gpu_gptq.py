@@ -353,3 +353,25 @@ def test_layer_streaming_equals_resident_execution():
     per_layer = sum(m.qweight.numel() for m in resident[0].modules() if isinstance(m, QuantLinear)) * 4
     assert streamer.resident_bytes() == 2 * per_layer
     assert all(m.qweight.numel() == 0 for b in blocks for m in b.modules() if isinstance(m, QuantLinear))
+
+
+@pytest.mark.parametrize("m", [1, 9, 32])
+def test_batch_launch_equals_single_launches(m):
+    """sb200_gptq4_matmul_batch: q / k / v (same input, three weight matrices of different N, one with a shorter K) in ONE
+    launch == three launches == the fp64 oracle; every ``out`` keeps the accumulate-in-place contract."""
+    from sparsebit_b200 import launch_count, ops
+
+    rng = np.random.default_rng(m)
+    probs, exps = [], []
+    for k, n in ((1024, 512), (1024, 132), (512, 256)):
+        x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, 128)
+        out = t(np.broadcast_to(bias, (m, n)).copy())
+        probs.append((t(x), t(qw), out, t(scales), t(zeros)))
+        exps.append(ogptq.dequant_matmul(x, qw, np.broadcast_to(bias, (m, n)), scales, zeros, 128))
+    before = launch_count()
+    outs = ops.gptq4_matmul_batch(probs, 128)
+    assert launch_count() - before == 1
+    for o, e in zip(outs, exps):
+        np.testing.assert_allclose(o.cpu().numpy(), e, **TOL)
+    with pytest.raises(RuntimeError, match="same number of tokens"):
+        ops.gptq4_matmul_batch([probs[0], (probs[1][0][:0].reshape(0, 1024).new_zeros(m + 1, 1024),) + probs[1][1:]], 128)
