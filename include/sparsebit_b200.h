@@ -299,6 +299,23 @@ int sb200_adaround_bwd(const float* x, const float* v, const float* scale, const
 int sb200_adaround_init(const float* x, const float* scale, float* v, int64_t outer,
                         int64_t channels, int64_t inner, void* stream);
 
+/* ---- (3c) DoReFa weight quantizer (sparsebit/quantization/quantizers/dorefa.py:15-26) ------
+ * The reference squashes the weights with tanh, divides by the abs-max of the result and hands that to STE.apply:
+ * five ATen passes (36 B/elem) in front of the fake-quant op, three more in autograd.  Here
+ *   absmax:  *absmax = max(*absmax, max |tanh(x)|), updated through its bit pattern (zero-initialise the float;
+ *            a NaN input leaves NaN, like torch.max)
+ *   fwd:     quantize = 0: out = tanh(x) / *absmax                      (what update_observer caches, dorefa.py:22-26)
+ *            quantize = 1: out = QDQ(tanh(x) / *absmax, scale, zero_point, qmin, qmax)      (dorefa.py:15-20)
+ *   bwd:     grad_x = ((grad_y * [qmin <= round(xn / scale) + zp <= qmax]) / *absmax) * (1 - tanh(x)^2)
+ * [outer, channels, inner] geometry as in (3b); scale / zero_point hold `channels` floats (buffers: no gradient). */
+int sb200_dorefa_absmax(const float* x, int64_t n, float* absmax, void* stream);
+int sb200_dorefa_fwd(const float* x, const float* absmax, const float* scale, const float* zero_point,
+                     float* out, int64_t outer, int64_t channels, int64_t inner, int qmin, int qmax,
+                     int quantize, void* stream);
+int sb200_dorefa_bwd(const float* x, const float* absmax, const float* scale, const float* zero_point,
+                     const float* grad_y, float* grad_x, int64_t outer, int64_t channels,
+                     int64_t inner, int qmin, int qmax, void* stream);
+
 /* ---- (4) GPTQ int4 group-wise dequant-matmul --------------------------------------------
  * Replaces cuda_kernel.vecquant4matmul / vecgroupquant4matmul
  * (large_language_models/llama/quantization/cuda/cuda_kernel.cpp:10-23,70,73;
@@ -375,6 +392,20 @@ int sb200_gptq4_set_impl(int impl);
  * drained accumulator, unpack warps waiting for a stage) sleep between mbarrier polls.  0 (default) = poll
  * continuously. */
 int sb200_gptq4_set_wait_backoff(int nanoseconds);
+
+/* Variant of the decode kernel (M <= 32; process-wide, tests / benchmarking only), a bit mask:
+ *   bit 0  the CTA's packed-weight slab is fetched with cp.async.bulk (one copy per packed row, all in flight before
+ *          the activations are touched; a multi-pass M reads the weights once) instead of per-lane LDG.128;
+ *   bit 1  the kernel is launched with programmatic stream serialisation: it requests its weights / scales / zeros
+ *          (constants of the model) while the previous kernel of the stream is still draining, and executes
+ *          griddepcontrol.wait before it reads the activations or touches `out`.
+ * Default 3.  Results are identical in every mode. */
+int sb200_gptq4_set_decode(int mode);
+
+/* Tuning knob of the per-group tcgen05 kernel (impl 2): how its epilogue warps drain the accumulator out of tensor
+ * memory.  1 (default) = pairs of tcgen05.ld.32x32b.x8, 0 = one .x16 per batch (round 1's form).  Same values either
+ * way; benchmarking only. */
+int sb200_gptq4_set_tc_drain(int narrow);
 
 /* Debug aid: when non-NULL, the tcgen05 kernel's CTA (0,0) writes clock64() stamps of its pipeline
  * handoffs into device_buffer[13][256] (event-major).  NULL disables tracing. */

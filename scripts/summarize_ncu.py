@@ -58,13 +58,25 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 
 
+def raw_page(name):
+    """Raw-metric page of a report as CSV text: from gpurun_out/<name>_<tag>.ncu-rep, or -- when the report itself was
+    too large to bring back from the GPU box -- from the gpurun_out/<name>_<tag>.csv exported there with the same command."""
+    import os
+
+    rep = f"gpurun_out/{name}_{tag}.ncu-rep"
+    if os.path.exists(rep):
+        return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    return open(f"gpurun_out/{name}_{tag}.csv").read()
+
+
 def report(name):
-    raw = subprocess.run(["ncu", "-i", f"gpurun_out/{name}_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = list(csv.reader(raw_page(name).splitlines()))
+    while rows and "Kernel Name" not in rows[0]:  # ncu banner lines in front of the header of an exported file
+        rows.pop(0)
     if len(rows) < 3:
         return f"# {name}: no data"
     hdr, units = rows[0], rows[1]
-    out = [f"# ncu --set full --clock-control none, report gpurun_out/{name}_{tag}.ncu-rep (summary of selected raw metrics)"]
+    out = [f"# ncu --clock-control none, report gpurun_out/{name}_{tag} (selected raw metrics per captured launch, in launch order)"]
     tens = [h for h in hdr if "tensor" in h and "pct_of_peak_sustained_active" in h and ".avg" in h]
     for r in rows[2:]:
         out.append("")
@@ -90,8 +102,9 @@ for name in names:
 def traffic():
     """dram__bytes_read + dram__bytes_write of the captured stream_kernel<TENSOR, STATS> launches over their
     algorithmic bytes (8 B/elem; grid-stride kernel: elements = the bench's first activation sites)."""
-    raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_qdq_stats_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = list(csv.reader(raw_page("prof_qdq_stats").splitlines()))
+    while rows and "Kernel Name" not in rows[0]:
+        rows.pop(0)
     hdr, units = rows[0], rows[1]
     rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

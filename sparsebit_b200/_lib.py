@@ -72,6 +72,9 @@ PROTOTYPES = {
     "sb200_adaround_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
     "sb200_adaround_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp]),
     "sb200_adaround_init": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "sb200_dorefa_absmax": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "sb200_dorefa_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp]),
+    "sb200_dorefa_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp]),
     "sb200_gptq4_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "sb200_gptq4_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_matmul_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
@@ -81,6 +84,8 @@ PROTOTYPES = {
     "sb200_gptq4_set_impl": (c_int, [c_int]),
     "sb200_gptq4_set_trace": (c_int, [c_vp]),
     "sb200_gptq4_set_wait_backoff": (c_int, [c_int]),
+    "sb200_gptq4_set_tc_drain": (c_int, [c_int]),
+    "sb200_gptq4_set_decode": (c_int, [c_int]),
 }
 
 SELECT_STATE_WORDS = 4

@@ -25,6 +25,8 @@ int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* sc
              cudaStream_t st, const __half* x_h = nullptr, __half* out_h = nullptr, const float* bias = nullptr);
 void gptq4_tc_set_trace(long long* p);
 void gptq4_tc_set_backoff(int ns);
+void gptq4_tc_set_drain(int narrow);
+void gptq4_decode_set_mode(int mode);
 int gptq_lowbit(int bits, const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                 long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
 static int g_gptq_impl = 0;
@@ -58,6 +60,18 @@ int sb200_gptq4_set_impl(int impl) {
 int sb200_gptq4_set_wait_backoff(int nanoseconds) {
   SB_REQUIRE(nanoseconds >= 0 && nanoseconds <= 100000, "sb200_gptq4_set_wait_backoff: 0..100000 ns (got %d)", nanoseconds);
   gptq4_tc_set_backoff(nanoseconds);
+  return SB200_OK;
+}
+
+int sb200_gptq4_set_decode(int mode) {
+  SB_REQUIRE(mode >= 0 && mode <= 3, "sb200_gptq4_set_decode: mode is a bit mask 0 .. 3 (bit 0 bulk-copy slab, bit 1 programmatic dependent launch; got %d)", mode);
+  gptq4_decode_set_mode(mode);
+  return SB200_OK;
+}
+
+int sb200_gptq4_set_tc_drain(int narrow) {
+  SB_REQUIRE(narrow == 0 || narrow == 1, "sb200_gptq4_set_tc_drain: 0 (tcgen05.ld .x16) or 1 (pairs of .x8) (got %d)", narrow);
+  gptq4_tc_set_drain(narrow);
   return SB200_OK;
 }
 

@@ -32,6 +32,17 @@ namespace sb200 {
 constexpr int kDecThreads = 128;  // 4 warps x 32 features
 constexpr int kDecCols = 128;
 constexpr int kDecBlockK = 128;
+// SLAB variant: the CTA's whole packed-weight slab ([blocks_per_slice x 16 packed rows] x 128 features) is requested
+// with one cp.async.bulk per packed row (thread t <-> row t, all issued in the first microsecond of the CTA's life,
+// completion on one mbarrier per 128-K block) instead of 2 x 4 LDG.128 per lane refilled between the MMA groups: every
+// byte the CTA will ever need is in flight before it touches the activations, it costs no registers, and a multi-pass
+// M (> 8 NB tokens) reads the weights from DRAM once.  Rows are 544 bytes apart in shared memory (512 + 32): the four
+// packed rows a quarter-warp reads with one LDS.128 then fall into disjoint bank groups.
+constexpr int kSlabRowBytes = kDecCols * 4 + 32;
+constexpr int kSlabGroupBytes = (kDecBlockK / 8) * kSlabRowBytes;
+__device__ __forceinline__ void dec_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <uint32_t MASK>
 __device__ __forceinline__ uint32_t dec_and_or(uint32_t x, uint32_t c) {
@@ -67,9 +78,16 @@ struct DecBatch {
 //   xh[8 NB][stride], xl[8 NB][stride] halves (stride = slice_k + 32: token rows start 64 bytes apart modulo 128, so the
 //   8 lanes of an LDS.128 phase hit distinct banks), xsum[8 NB][blocks_per_slice] floats, escale[8 NB] floats,
 //   scale / zeros [blocks_per_slice][128] floats each.
-template <int NB>
+//   SLAB: the packed-weight slab [blocks_per_slice][16][544 B] comes first, and only x_rows = min(M, 8 NB) token rows
+//   are allocated for xh / xl / xsum (MMA token columns beyond the real tokens re-read the last real row; their results
+//   are never written back).
+// pdl: launched with programmatic stream serialisation -- the next kernel of the stream may start while this one runs
+// (griddepcontrol.launch_dependents) and this one touches nothing a predecessor may still be writing (the activations,
+// `out`) before griddepcontrol.wait; the packed weights, scales and zeros are constants of the model and are requested
+// before the wait, so their DRAM latency overlaps the tail of the previous linear.
+template <int NB, bool SLAB>
 __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_constant__ DecBatch batch, int M,
-                                                                 int blocks_per_slice) {
+                                                                 int blocks_per_slice, int x_rows, int pdl) {
   extern __shared__ __align__(16) unsigned char dsm[];
   constexpr int MT = 8 * NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -91,14 +109,17 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
   const int nb = min(b0 + blocks_per_slice, nblk) - b0;
   const int slice_k = blocks_per_slice * kDecBlockK;
   const int stride = slice_k + 32;  // halves
-  __half* xh = reinterpret_cast<__half*>(dsm);
-  __half* xl = xh + MT * stride;
-  float* xsum = reinterpret_cast<float*>(xl + MT * stride);
-  float* escale = xsum + MT * blocks_per_slice;
+  const int x_alloc = SLAB ? x_rows : MT;  // token rows held in shared memory
+  const unsigned char* slab = dsm;
+  __half* xh = reinterpret_cast<__half*>(dsm + (SLAB ? (size_t)blocks_per_slice * kSlabGroupBytes : 0));
+  __half* xl = xh + x_alloc * stride;
+  float* xsum = reinterpret_cast<float*>(xl + x_alloc * stride);
+  float* escale = xsum + x_alloc * blocks_per_slice;
   float* s_sc = escale + MT;                          // [blocks_per_slice][128] scale of (block, feature of this CTA)
   float* s_zr = s_sc + blocks_per_slice * kDecCols;   // [blocks_per_slice][128] zeros
   __shared__ int s_need_lo;
   __shared__ unsigned int s_amax[32];
+  __shared__ __align__(8) uint64_t s_bar[8];  // SLAB: one per 128-K block of the slice (blocks_per_slice <= 8)
   const int nbase = bx * kDecCols + warp * 32 + 4 * g;  // this lane's four features nbase .. nbase + 3
   const bool col_ok = nbase < N;                                  // N % 4 == 0: all four or none
   uint32_t bias;
@@ -114,6 +135,32 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     }
   };
 
+  uint4 wa[4], wb[4];
+  if (SLAB) {
+    if (tid < nb) mbar_init(&s_bar[tid], kDecBlockK / 8);  // every row thread of a block arrives exactly once
+    mbar_fence_init();
+    __syncthreads();
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int bl = tid >> 4, r = tid & 15;
+    if (bl < nb) {
+      const int row = (b0 + bl) * (kDecBlockK / 8) + r;
+      unsigned char* dst = dsm + (size_t)(bl * (kDecBlockK / 8) + r) * kSlabRowBytes;
+      const int col0 = bx * kDecCols;
+      const uint32_t bytes = (uint32_t)min(kDecCols, N - col0) * 4u;  // N % 4 == 0: a multiple of 16
+      if (row < KW) {
+        mbar_expect_tx(&s_bar[bl], bytes);
+        tma_bulk_g2s(dst, qw + (size_t)row * N + col0, bytes, &s_bar[bl]);
+      } else {  // K % 128 != 0: rows past the packed matrix contribute nothing
+        for (int j = 0; j < kDecCols / 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(0u, 0u, 0u, 0u);
+        dec_mbar_arrive(&s_bar[bl]);
+      }
+    }
+  } else {
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    load_group(0, wa);
+    if (nb > 1) load_group(1, wb);
+  }
+
   // scales / zeros of this CTA's 128 features for every 128-K block of its slice: thread = feature, so the table is
   // read with one request per (feature, block) instead of one per (lane, feature, block) -- the [N, G] checkpoint layout
   // puts consecutive features G floats apart, and fetching them lane by lane inside the group loop cost 4x the sectors
@@ -127,12 +174,17 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     }
   }
 
+  // everything above reads constants of the model; from here on the activations and `out` of this call are touched
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+
   for (int m0 = 0; m0 < M; m0 += MT) {
-    // The kernel lives for a few microseconds, i.e. a handful of DRAM latencies: the packed weights of the first two
-    // 128-K blocks are requested before anything else, so their latency overlaps the staging of the activations.
-    uint4 wa[4], wb[4];
-    load_group(0, wa);
-    if (nb > 1) load_group(1, wb);
+    // The kernel lives for a few microseconds, i.e. a handful of DRAM latencies: the packed weights (the whole slab,
+    // or the first two 128-K blocks of the register-staged variant) were requested before anything else, so their
+    // latency overlaps the staging of the activations.
+    if (!SLAB && m0 > 0) {
+      load_group(0, wa);
+      if (nb > 1) load_group(1, wb);
+    }
     __syncthreads();  // the previous pass is done with the staging buffers
     const int tokens = min(MT, M - m0);  // real tokens of this pass; the other token columns of the MMA are never read back
     if (tid < MT) s_amax[tid] = 0u;
@@ -195,7 +247,10 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[T][q][j] = 0.f;
 
+    // token row of MMA column block q for this lane (SLAB: rows beyond the real tokens alias the last real one)
+    auto trow = [&](int r) { return SLAB ? min(r, tokens - 1) : r; };
     auto compute_group = [&](int bl, const uint4 (&w)[4]) {
+      if (SLAB) mbar_wait(&s_bar[bl], 0u);  // phase 0 = the slab rows of this block have landed (stays true afterwards)
       float d[2][NB][4];
 #pragma unroll
       for (int T = 0; T < 2; ++T)
@@ -210,10 +265,13 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
         const int koff = (bl * 4 + ch) * 32 + 8 * c;
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
-          bh[q] = *reinterpret_cast<const uint4*>(xh + (q * 8 + g) * stride + koff);
-          if (need_lo) bl4[q] = *reinterpret_cast<const uint4*>(xl + (q * 8 + g) * stride + koff);
+          bh[q] = *reinterpret_cast<const uint4*>(xh + trow(q * 8 + g) * stride + koff);
+          if (need_lo) bl4[q] = *reinterpret_cast<const uint4*>(xl + trow(q * 8 + g) * stride + koff);
         }
-        const uint32_t words[4] = {w[ch].x, w[ch].y, w[ch].z, w[ch].w};  // features nbase + 0..3
+        const uint4 wv = SLAB ? *reinterpret_cast<const uint4*>(slab + (size_t)(bl * (kDecBlockK / 8) + 4 * ch + c) * kSlabRowBytes +
+                                                                (warp * 32 + 4 * g) * 4)
+                              : w[ch];
+        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};  // features nbase + 0..3
 #pragma unroll
         for (int T = 0; T < 2; ++T) {
           uint32_t a0[4], a1[4];  // A fragments of MMA i = 0 and i = 1
@@ -249,7 +307,7 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
         const float sA = s_sc[f], zA = s_zr[f], sB = s_sc[f + 1], zB = s_zr[f + 1];
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
-          const float xs0 = xsum[(q * 8 + 2 * c) * blocks_per_slice + bl], xs1 = xsum[(q * 8 + 2 * c + 1) * blocks_per_slice + bl];
+          const float xs0 = xsum[trow(q * 8 + 2 * c) * blocks_per_slice + bl], xs1 = xsum[trow(q * 8 + 2 * c + 1) * blocks_per_slice + bl];
           acc[T][q][0] += fmaf(sA, d[T][q][0], -zA * xs0);
           acc[T][q][1] += fmaf(sA, d[T][q][1], -zA * xs1);
           acc[T][q][2] += fmaf(sB, d[T][q][2], -zB * xs0);
@@ -259,10 +317,10 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     };
     for (int bl = 0; bl < nb; bl += 2) {
       compute_group(bl, wa);
-      if (bl + 2 < nb) load_group(bl + 2, wa);
+      if (!SLAB && bl + 2 < nb) load_group(bl + 2, wa);
       if (bl + 1 < nb) {
         compute_group(bl + 1, wb);
-        if (bl + 3 < nb) load_group(bl + 3, wb);
+        if (!SLAB && bl + 3 < nb) load_group(bl + 3, wb);
       }
     }
     if (col_ok) {
@@ -282,6 +340,31 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
 
 bool gptq4_decode_supported(const int32_t* qweight, long long N) { return (N % 4 == 0) && aligned16(qweight); }
 
+// Decode-kernel variant (process-wide benchmarking / test switch, sb200_gptq4_set_decode): bit 0 = bulk-copy weight
+// slab (SLAB), bit 1 = programmatic dependent launch.
+static int g_dec_mode = 3;
+void gptq4_decode_set_mode(int mode) { g_dec_mode = mode; }
+int gptq4_decode_get_mode() { return g_dec_mode; }
+
+template <int NB, bool SLAB>
+static int dec_launch(const DecBatch& batch, dim3 grid, size_t smem, int M, int S, int x_rows, bool pdl, cudaStream_t st) {
+  static std::atomic<int> attr_done[64];
+  if (smem > 48 * 1024) SB_CUDA(ensure_dyn_smem(gptq4_decode_kernel<NB, SLAB>, (int)smem, attr_done));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SB_CUDA(cudaLaunchKernelEx(&cfg, gptq4_decode_kernel<NB, SLAB>, batch, M, S, x_rows, pdl ? 1 : 0));
+  SB_LAUNCHED();
+  return SB200_OK;
+}
+
 // `count` problems sharing M in one launch (count == 1: the plain entry point)
 int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStream_t st) {
   DecBatch batch;
@@ -296,6 +379,7 @@ int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStre
   }
   for (int i = count; i < kDecMaxProblems; ++i) batch.p[i] = batch.p[0];
   const int nbk = M <= 8 ? 1 : (M <= 16 ? 2 : 4);
+  const bool slab = (g_dec_mode & 1) != 0, pdl = (g_dec_mode & 2) != 0;
   // K slices: ~5 CTAs per SM (what the register file holds: 4 warps x 96 registers), each streaming as long a K
   // range as that allows, bounded by the activation slice held in shared memory
   int want = (sm_count() * 5 + colblocks - 1) / colblocks;
@@ -307,15 +391,15 @@ int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStre
   const int slices = (nblk_max + S - 1) / S;
   const dim3 grid((unsigned)colblocks, (unsigned)slices);
   const int mt = 8 * nbk;
-  const size_t smem = (size_t)2 * mt * (S * kDecBlockK + 32) * sizeof(__half) + (size_t)mt * S * sizeof(float) + (size_t)mt * sizeof(float) +
-                      (size_t)2 * S * kDecCols * sizeof(float);
-#define SB_GO(NB_) gptq4_decode_kernel<NB_><<<grid, kDecThreads, smem, st>>>(batch, (int)M, S)
-  if (nbk == 1) SB_GO(1);
-  else if (nbk == 2) SB_GO(2);
-  else SB_GO(4);
+  const int x_rows = slab ? (int)(M < mt ? M : mt) : mt;
+  const size_t smem = (slab ? (size_t)S * kSlabGroupBytes : 0) + (size_t)2 * x_rows * (S * kDecBlockK + 32) * sizeof(__half) +
+                      (size_t)x_rows * S * sizeof(float) + (size_t)mt * sizeof(float) + (size_t)2 * S * kDecCols * sizeof(float);
+#define SB_GO(NB_) (slab ? dec_launch<NB_, true>(batch, grid, smem, (int)M, S, x_rows, pdl, st) \
+                         : dec_launch<NB_, false>(batch, grid, smem, (int)M, S, x_rows, pdl, st))
+  if (nbk == 1) return SB_GO(1);
+  if (nbk == 2) return SB_GO(2);
+  return SB_GO(4);
 #undef SB_GO
-  SB_LAUNCHED();
-  return SB200_OK;
 }
 
 int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,

@@ -160,7 +160,7 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 const __grid_constant__ CUtensorMap map_q, float* __restrict__ out, const float* __restrict__ scales,
                 const float* __restrict__ zeros, const float* __restrict__ xsum, const float* __restrict__ rowscale,
                 const __half* __restrict__ zint, const int* __restrict__ int_zero_flag, int M, int K, int N, int Gq,
-                int G128, int group_size, long long* __restrict__ trace, int backoff_ns) {
+                int G128, int group_size, long long* __restrict__ trace, int backoff_ns, int narrow_drain) {
   extern __shared__ unsigned char smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), bookkeeping after them
   unsigned char* stage_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -425,16 +425,20 @@ gptq4_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       // TMEM (the drain is the paced resource of this kernel: 64 KB per group at 64 B/clk).  tcgen05.wait::ld
       // covers every outstanding load, so each load is issued right after the wait for the previous one.
       uint32_t pa[16], pb[16];
-      tc_ld16(taddr, pa);
+      auto ld16 = [&](uint32_t addr, uint32_t (&p)[16]) {  // warp-uniform choice: .x16, or the same columns as two .x8
+        if (narrow_drain) tc_ld16_narrow(addr, p);
+        else tc_ld16(addr, p);
+      };
+      ld16(taddr, pa);
       tc_wait_ld16(pa);
       if (e == 0) SB_TRACE(10, g);
-      tc_ld16(taddr + 16, pb);
+      ld16(taddr + 16, pb);
       fold(0, pa);
       tc_wait_ld16(pb);
-      tc_ld16(taddr + 32, pa);
+      ld16(taddr + 32, pa);
       fold(1, pb);
       tc_wait_ld16(pa);
-      tc_ld16(taddr + 48, pb);
+      ld16(taddr + 48, pb);
       fold(2, pa);
       tc_wait_ld16(pb);
       if (e == 0) SB_TRACE(11, g);
@@ -509,6 +513,8 @@ static long long* g_tc_trace = nullptr;
 void gptq4_tc_set_trace(long long* p) { g_tc_trace = p; }
 static int g_tc_backoff_ns = 0;
 void gptq4_tc_set_backoff(int ns) { g_tc_backoff_ns = ns; }
+static int g_tc_narrow_drain = 1;
+void gptq4_tc_set_drain(int narrow) { g_tc_narrow_drain = narrow; }
 
 bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
                         long long KW, int group_size) {
@@ -569,7 +575,7 @@ int gptq4_tc(const float* x, const int32_t* qweight, float* out, const float* sc
   const dim3 grid((unsigned)((M + kTileM - 1) / kTileM), (unsigned)((N + kTileN - 1) / kTileN));
   gptq4_tc_kernel<<<grid, kTcThreads, smem, st>>>(map_hi, map_lo, map_q, out, scales, zeros, xsum, rowscale, zint, flag,
                                                   (int)M, (int)K, (int)N, Gq, G128, group_size, g_tc_trace,
-                                                  g_tc_backoff_ns);
+                                                  g_tc_backoff_ns, g_tc_narrow_drain);
   SB_LAUNCHED();
   return SB200_OK;
 }

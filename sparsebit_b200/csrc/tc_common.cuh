@@ -95,6 +95,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// the same 16 columns as two .x8 loads issued back to back (the narrow forms pipeline through the TMEM read port far
+// better than the wide ones: 256 B/clk/SM for .x8 pairs against 52 for .x16, profiles/r02_tmem_probe*.jsonl)
+__device__ __forceinline__ void tc_ld16_narrow(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr), "r"(taddr + 8)
+      : "memory");
+}
 // wait for the outstanding tcgen05.ld; the registers are threaded through the statement so that no use of them
 // can be scheduled above the wait
 __device__ __forceinline__ void tc_wait_ld16(uint32_t (&r)[16]) {

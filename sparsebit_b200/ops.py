@@ -214,6 +214,54 @@ def moments_update(x2d, out, centre=None):
     return out
 
 
+# ----------------------------------------------------------------------------- DoReFa
+def dorefa_absmax(x):
+    """max |tanh(x)| as a one-element float tensor (dorefa.py:16-17), one 4 B/elem pass."""
+    lib = _lib.load()
+    _req(x, "data")
+    m = torch.zeros(1, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.sb200_dorefa_absmax(x.data_ptr(), x.numel(), m.data_ptr(), _stream(x)))
+    return m
+
+
+def dorefa_forward(x, absmax, scale=None, zero_point=None, qmin=0, qmax=0, ch_axis=None):
+    """tanh(x) / absmax, fake-quantised when qparams are given (dorefa.py:15-20); without them the normalised tensor
+    the observer sees (dorefa.py:22-26)."""
+    lib = _lib.load()
+    _req(x, "data"), _req(absmax, "absmax")
+    quantize = scale is not None
+    if quantize:
+        _req(scale, "scale"), _req(zero_point, "zero_point")
+        outer, c, inner = _adaround_geometry(x, scale, ch_axis)
+        if zero_point.numel() != c:
+            raise SparsebitB200Error(f"dorefa: qparams need {c} elements (got {zero_point.numel()})")
+    else:
+        outer, c, inner = 1, 1, x.numel()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.sb200_dorefa_fwd(x.data_ptr(), absmax.data_ptr(), scale.data_ptr() if quantize else None,
+                                   zero_point.data_ptr() if quantize else None, out.data_ptr(), outer, c, inner,
+                                   int(qmin), int(qmax), int(quantize), _stream(x)))
+    return out
+
+
+def dorefa_backward(x, absmax, scale, zero_point, grad_y, qmin, qmax, ch_axis=None):
+    """Gradient of dorefa_forward with respect to x (STE mask -> / absmax -> tanh'), one 12 B/elem pass."""
+    lib = _lib.load()
+    _req(x, "data"), _req(absmax, "absmax"), _req(scale, "scale"), _req(zero_point, "zero_point"), _req(grad_y, "grad")
+    if grad_y.shape != x.shape:
+        raise SparsebitB200Error("dorefa: grad_y must have the shape of data")
+    outer, c, inner = _adaround_geometry(x, scale, ch_axis)
+    if zero_point.numel() != c:
+        raise SparsebitB200Error(f"dorefa: qparams need {c} elements (got {zero_point.numel()})")
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.sb200_dorefa_bwd(x.data_ptr(), absmax.data_ptr(), scale.data_ptr(), zero_point.data_ptr(), grad_y.data_ptr(),
+                                   gx.data_ptr(), outer, c, inner, int(qmin), int(qmax), _stream(x)))
+    return gx
+
+
 # ----------------------------------------------------------------------------- AdaRound
 def _adaround_geometry(x, scale, ch_axis):
     if ch_axis is None:

@@ -58,11 +58,15 @@ def trt_fake_quant(x_f, scale, zero_point, qdesc):
     """quant_tensor.py:128-156: TensorRT only supports symmetric quantisation.  The reference
     asserts ``abs(zero_point).sum() == 0`` with a device sync on every call (:132-134); here the
     check is done once per zero_point tensor version."""
+    check_trt_symmetric(zero_point)
+    return ort_fake_quant(x_f, scale, zero_point, qdesc)
+
+
+def check_trt_symmetric(zero_point):
     key = (zero_point.data_ptr(), zero_point._version)
     if getattr(trt_fake_quant, "_ok_key", None) != key:
         assert float(zero_point.abs().sum()) == 0, "tensorrt only support symmetric quant, but zp={}".format(zero_point)
         trt_fake_quant._ok_key = key
-    return ort_fake_quant(x_f, scale, zero_point, qdesc)
 
 
 fake_quant_factory = {

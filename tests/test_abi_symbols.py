@@ -95,3 +95,11 @@ def test_widened_entry_points_validate_before_launching():
     assert lib.sb200_observe_moments(p, 3, 16385, None, p, p, 8, None) == -1 and b"workspace" in lib.sb200_last_error()
     assert lib.sb200_gptq4_set_wait_backoff(-1) == -1
     assert lib.sb200_gptq4_set_wait_backoff(0) == 0
+    # DoReFa (dorefa.py:15-26): null / empty / bad flags
+    assert lib.sb200_dorefa_absmax(p, 0, p, None) == -1 and b"empty" in lib.sb200_last_error()
+    assert lib.sb200_dorefa_absmax(None, 8, p, None) == -1
+    assert lib.sb200_dorefa_fwd(p, p, p, p, p, 1, 1, 8, -8, 7, 2, None) == -1 and b"quantize" in lib.sb200_last_error()
+    assert lib.sb200_dorefa_fwd(p, p, None, p, p, 1, 1, 8, -8, 7, 1, None) == -1 and b"qparams" in lib.sb200_last_error()
+    assert lib.sb200_dorefa_fwd(p, p, p, p, p, 1, 1, 8, 7, -8, 1, None) == -1
+    assert lib.sb200_dorefa_bwd(p, p, p, p, None, p, 1, 1, 8, -8, 7, None) == -1
+    assert lib.sb200_dorefa_bwd(p, p, p, p, p, p, 1, 0, 8, -8, 7, None) == -1

@@ -118,9 +118,21 @@ DECODE_CASES = [(1, 4096, 4096, 128), (8, 1024, 512, 128), (9, 1024, 260, 128), 
                 (32, 1536, 384, 384), (33, 1000, 256, -1), (70, 328, 64, -1), (1, 11008, 4096, 128), (5, 6656, 2516, -1)]
 
 
+@pytest.fixture
+def decode_mode():
+    """sb200_gptq4_set_decode is process-wide: restore the default (3 = bulk-copy slab + programmatic launch) afterwards."""
+    from sparsebit_b200 import _lib
+
+    lib = _lib.load()
+    yield lambda mode: _lib.check(lib.sb200_gptq4_set_decode(mode))
+    _lib.check(lib.sb200_gptq4_set_decode(3))
+
+
 @pytest.mark.parametrize("m,k,n,gs", DECODE_CASES)
 @pytest.mark.parametrize("fp16_acts", [False, True])
-def test_decode_hmma_path_vs_fp64_oracle(m, k, n, gs, fp16_acts):
+@pytest.mark.parametrize("mode", [3, 1, 0])  # slab + PDL (default), slab alone, register-staged LDG.128 variant
+def test_decode_hmma_path_vs_fp64_oracle(m, k, n, gs, fp16_acts, mode, decode_mode):
+    decode_mode(mode)
     rng = np.random.default_rng(13 * k + n + m)
     x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, gs)
     if fp16_acts:
@@ -353,6 +365,56 @@ def test_layer_streaming_equals_resident_execution():
     per_layer = sum(m.qweight.numel() for m in resident[0].modules() if isinstance(m, QuantLinear)) * 4
     assert streamer.resident_bytes() == 2 * per_layer
     assert all(m.qweight.numel() == 0 for b in blocks for m in b.modules() if isinstance(m, QuantLinear))
+
+
+@pytest.mark.parametrize("mode", [3, 2, 0])
+@pytest.mark.parametrize("graph", [False, True])
+def test_decode_chain_of_dependent_linears_under_programmatic_launch(mode, graph, decode_mode):
+    """y1 = W1 x, y2 = W2 y1, y3 = W3 y2 launched back to back on one stream: with programmatic dependent launch a
+    kernel may start (and fetch its weights) before its predecessor has finished, and must still see the predecessor's
+    complete output (griddepcontrol.wait in front of the activation staging).  Also as a captured CUDA graph."""
+    from sparsebit_b200 import ops
+
+    decode_mode(mode)
+    rng = np.random.default_rng(5)
+    dims = [(1024, 768), (768, 1536), (1536, 256)]
+    m = 3
+    layers = []
+    for k, n in dims:
+        _, qw, _, scales, zeros = _make_case(rng, (m,), k, n, 128)
+        layers.append((t(qw), t(scales), t(zeros), qw, scales, zeros))
+    x = rng.standard_normal((m, dims[0][0])).astype(np.float32)
+    ys = [torch.zeros(m, n, device=dev()) for _, n in dims]
+
+    def chain(xin):
+        for y in ys:
+            y.zero_()
+        cur = xin
+        for (qw, sc, zr, *_), y in zip(layers, ys):  # three decode kernels back to back, each reading its predecessor's out
+            ops.gptq4_matmul(cur, qw, y, sc, zr, 128, impl=1)
+            cur = y
+
+    xt = t(x)
+    if graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            chain(xt)  # warm-up outside the capture
+        torch.cuda.current_stream().wait_stream(s)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            chain(xt)
+        for _ in range(3):
+            gr.replay()
+    else:
+        for _ in range(3):
+            chain(xt)
+    torch.cuda.synchronize()
+    exp = x.astype(np.float64)
+    for (_, _, _, qw, scales, zeros), (k, n) in zip(layers, dims):
+        exp = ogptq.dequant_matmul(exp.astype(np.float32), qw, np.zeros((m, n)), scales, zeros, 128)
+    got = ys[-1].cpu().numpy()
+    np.testing.assert_allclose(got, exp, rtol=2e-4, atol=2e-4 * np.abs(exp).max())  # three chained fp32 linears vs fp64
 
 
 @pytest.mark.parametrize("m", [1, 9, 32])

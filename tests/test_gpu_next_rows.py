@@ -238,3 +238,75 @@ def test_pact_fused_clamp_gradients_equal_autograd_through_clamp(scheme, bit):
     assert torch.equal(xr.grad, x2.grad)
     ref_ga = float(alpha.grad)
     assert abs(float(q.alpha.grad) - ref_ga) <= 1e-5 * max(1.0, float(gy.abs().sum()) * 1e-2)
+
+
+def _dorefa_eager(x, scale, zp, qdesc_q):
+    """The reference op chain on the GPU (dorefa.py:15-20): ATen tanh / abs / max / div, then STE (native QDQ)."""
+    from sparsebit_b200.quantization.quantizers.quant_tensor import STE
+
+    t_ = x.tanh()
+    xn = t_ / t_.detach().abs().max()
+    return xn, STE.apply(xn, scale, zp, qdesc_q.qdesc, qdesc_q.backend)
+
+
+@pytest.mark.parametrize("scheme,shape", [("per-tensor-symmetric", (64, 3, 7, 7)), ("per-tensor-affine", (33, 5, 3)),
+                                          ("per-channel-symmetric", (48, 16, 3, 3)), ("per-channel-affine", (10, 1031))])
+def test_dorefa_fused_kernels_match_the_eager_chain(scheme, shape):
+    """sb200_dorefa_absmax / _fwd / _bwd against tanh -> / max|.| -> STE run as separate ATen ops + autograd: the
+    normalised tensor to 1 ulp, fake-quantised values and gradients equal except where that ulp moves a rounding."""
+    from sparsebit_b200 import ops
+
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = (torch.randn(shape, generator=g) * 1.3).to(dev())
+    q = build_quantizer(sbcfg.quantizer_config(scheme, 4, "weight", qtype="dorefa")).to(dev())
+    q.set_backend(Backend.VIRTUAL)
+    q.update_observer(x)
+    q.calc_qparams()
+    q.enable_quant()
+    assert len(q.observer.data_cache) == 0
+    # what the observer saw: tanh(x) / max|tanh(x)|, so min / max lie in [-1, 1] and one of them is +-1
+    m = ops.dorefa_absmax(x)
+    assert abs(float(m) - float(x.tanh().abs().max())) <= 1.2e-7  # libdevice tanhf on both sides (1 ulp of slack below 1.0)
+    xn_fused = ops.dorefa_forward(x, m)
+    xr = x.clone().requires_grad_(True)
+    xn, y_eager = _dorefa_eager(xr, q.scale, q.zero_point, q)
+    np.testing.assert_allclose(xn_fused.cpu().numpy(), xn.detach().cpu().numpy(), rtol=5e-7, atol=0)
+    assert float(xn_fused.abs().max()) == 1.0
+    gy = torch.randn(shape, generator=g).to(dev())
+    y_eager.backward(gy)
+    xf = x.clone().requires_grad_(True)
+    y = q(xf)
+    y.backward(gy)
+    a, b = y.detach().cpu().numpy(), y_eager.detach().cpu().numpy()
+    assert np.mean(a != b) < 2e-3, (scheme, np.mean(a != b))
+    ga, gb = xf.grad.cpu().numpy(), xr.grad.cpu().numpy()
+    assert np.mean(~np.isclose(ga, gb, rtol=1e-5, atol=1e-8)) < 2e-3, scheme
+    # on-grid: every output is (k - zp) * scale for an integer k in [qmin, qmax]
+    qmin, qmax = q.qdesc.qrange
+    s = q.scale.detach().reshape([-1] + [1] * (len(shape) - 1)).cpu().numpy() if q.scale.numel() > 1 else float(q.scale)
+    z = q.zero_point.detach().reshape([-1] + [1] * (len(shape) - 1)).cpu().numpy() if q.scale.numel() > 1 else float(q.zero_point)
+    k = a / s + np.rint(z)
+    assert np.abs(k - np.rint(k)).max() < 1e-3 and k.min() >= qmin - 1e-3 and k.max() <= qmax + 1e-3
+
+
+def test_dorefa_nan_and_ragged_inputs():
+    from sparsebit_b200 import ops
+
+    x = torch.randn(1025, device=dev())[1:]  # 4-byte aligned only, odd length: scalar paths
+    m = ops.dorefa_absmax(x)
+    assert abs(float(m) - float(x.tanh().abs().max())) <= 1.2e-7
+    s, z = torch.tensor([0.125], device=dev()), torch.tensor([0.0], device=dev())
+    xc = x.contiguous()
+    y = ops.dorefa_forward(xc, m, s, z, -8, 7)
+    ref = torch.clamp(torch.round((xc.tanh() / m) / s), -8, 7) * s
+    assert np.mean(y.cpu().numpy() != ref.cpu().numpy()) < 2e-3
+    xb = xc.clone()
+    xb[5] = float("nan")
+    mb = ops.dorefa_absmax(xb)
+    assert torch.isnan(mb).all()  # torch.max propagates NaN; every normalised value is then NaN, like the reference
+    assert torch.isnan(ops.dorefa_forward(xb, mb, s, z, -8, 7)).all()
+    gx = ops.dorefa_backward(xc, m, s, z, torch.ones_like(xc), -8, 7)
+    t_ = xc.tanh()
+    vq = torch.round((t_ / m) / s)
+    exp = torch.where((vq >= -8) & (vq <= 7), torch.ones_like(xc), torch.zeros_like(xc)) / m * (1 - t_ * t_)
+    assert np.mean(~np.isclose(gx.cpu().numpy(), exp.cpu().numpy(), rtol=1e-5, atol=1e-8)) < 2e-3
