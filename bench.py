@@ -669,13 +669,14 @@ def main():
         if rc:
             _lib.check(rc, "qdq_stats")
 
+    # the 54 weight quantizers of the model run as ONE launch (sb200_qdq_multi_plan once, sb200_qdq_multi_run per step):
+    # single layers are L2-resident and launch-bound when issued one by one (54 launches: 0.076 of the HBM roofline)
+    from sparsebit_b200 import ops as _sbops
+
+    w_plan = _sbops.QdqMulti([dict(x=w[0], out=w[1], scale=w[2], zero_point=w[3], qmin=-128, qmax=127) for w in weights])
+
     def enqueue_weights(stream):
-        rc = 0
-        for w in weights:
-            rc |= lib.sb200_qdq_perchannel_fwd(w[0].data_ptr(), w[2].data_ptr(), w[3].data_ptr(), w[1].data_ptr(), 1, w[0].shape[0],
-                                               numel(w[0].shape[1:]), -128, 127, 0, stream)
-        if rc:
-            _lib.check(rc, "qdq_perchannel")
+        _lib.check(lib.sb200_qdq_multi_run(w_plan.table.data_ptr(), w_plan.count, w_plan.total_rows, stream), "qdq_multi_run")
 
     # The 109 launches of a step are captured once into two CUDA graphs (activation sites, weight
     # sites) and replayed: the step is a launch-bound inner loop from the host's point of view.
@@ -883,7 +884,8 @@ def main():
             dec_bytes = 6_476_005_376 / 2 + 2 * 4 * 6_476_005_376 / 128  # packed int4 + fp32 scales and zeros (g128)
             gptq = {"config": "LLaMA-7B, all 32 x 7 linears, int4 g128, fp16->fp32 activations, CUDA-graph timed, synthetic packed weights",
                     "decode_tok_s": 1.0 / t_dec, "decode_tok_s_one_launch_per_linear": 1.0 / totals[(1, "ours_auto")],
-                    "decode_launches": "q/k/v and gate/up fused into one launch each (sb200_gptq4_matmul_batch): 4 launches per layer",
+                    "decode_launches": "q/k/v and gate/up fused into one launch each (sb200_gptq4_matmul_batch_ex): 4 launches per layer, "
+                                       "programmatic dependent launch, SB200_GPTQ4_STATIC_WEIGHTS (model weights are constants)",
                     "prefill_2048_tok_s": 2048.0 / t_pre,
                     "prefill_2048_useful_TFLOPs": flops_tok * 2048 / t_pre / 1e12,
                     "roofline_prefill": {"bound": "tensor", "achieved": flops_tok * 2048 / t_pre / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
@@ -974,7 +976,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": bs * world, "act_elems_per_gpu": act_elems, "weight_elems_per_gpu": w_elems,
                        "parallelism": f"replicas x{world} (path has no exchange step; no data-path collective)",
                        "l2": "inputs larger than L2: 22 GB working set per step, every site owns its in/out buffers",
-                       "launch": "2 CUDA graphs (55 activation sites + 1 init; 54 weight sites) replayed per step" if use_graphs else "eager launches"},
+                       "launch": "2 CUDA graphs (55 activation launches + 1 state init; the 54 weight sites in ONE multi-tensor launch) replayed per step"
+                                 if use_graphs else "eager launches (55 activation launches + 1 init + 1 multi-tensor weight launch)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "gptq": gptq, **extra,
         }
         print(json.dumps(line))

@@ -339,10 +339,16 @@ int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const
  * 3 = tcgen05 with the scaled weights as two fp16 planes written to tensor memory (A operand) and whole-K
  * accumulation, drained into fp32 registers every chunk_k K (multiple of 64; 0 = default 512) to bound the
  * tensor core's truncating accumulation. */
+/* flags: SB200_GPTQ4_STATIC_WEIGHTS -- the caller guarantees that qweight / scales / zeros are constants of the model,
+ * i.e. NOT written by the kernel immediately in front of this call on the stream.  The decode kernel (M <= 32) is
+ * launched programmatically dependent (it may begin while its predecessor drains); with this flag it requests the
+ * weights before it waits for the predecessor, without it nothing is read before the wait (plain stream semantics). */
+#define SB200_GPTQ4_STATIC_WEIGHTS 1
 typedef struct sb200_gptq4_options {
   int impl;
   int chunk_k;
-  int reserved[6]; /* must be zero */
+  int flags;
+  int reserved[5]; /* must be zero */
 } sb200_gptq4_options;
 int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, const float* scales,
                           const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows,
@@ -362,6 +368,8 @@ typedef struct sb200_gptq4_problem {
   int group_size;          /* 0 = k */
 } sb200_gptq4_problem;
 int sb200_gptq4_matmul_batch(const sb200_gptq4_problem* problems, int count, int64_t m, void* stream);
+/* The same with flags (SB200_GPTQ4_STATIC_WEIGHTS, see sb200_gptq4_options). */
+int sb200_gptq4_matmul_batch_ex(const sb200_gptq4_problem* problems, int count, int64_t m, int flags, void* stream);
 
 /* fp16 activations in, fp16 result out, WITHOUT the per-call casts of QuantLinear.forward (utils/quant.py:262-278 casts
  * x / scales / zeros / bias to fp32, materialises y = bias, and casts the result back):
@@ -396,10 +404,15 @@ int sb200_gptq4_set_wait_backoff(int nanoseconds);
 /* Variant of the decode kernel (M <= 32; process-wide, tests / benchmarking only), a bit mask:
  *   bit 0  the CTA's packed-weight slab is fetched with cp.async.bulk (one copy per packed row, all in flight before
  *          the activations are touched; a multi-pass M reads the weights once) instead of per-lane LDG.128;
- *   bit 1  the kernel is launched with programmatic stream serialisation: it requests its weights / scales / zeros
- *          (constants of the model) while the previous kernel of the stream is still draining, and executes
- *          griddepcontrol.wait before it reads the activations or touches `out`.
- * Default 3.  Results are identical in every mode. */
+ *   bit 1  the kernel is launched with programmatic stream serialisation (it may begin while the previous kernel of
+ *          the stream drains; griddepcontrol.wait before the first global read, or -- SB200_GPTQ4_STATIC_WEIGHTS --
+ *          after the weights / scales / zeros have been requested);
+ *   bit 3  treat every call as SB200_GPTQ4_STATIC_WEIGHTS (benchmarking the flag through entry points without one);
+ *   bit 2  (register-staged variant) the 128-K blocks beyond the two a lane holds in registers are prefetched into L2
+ *          at the start of the CTA, so the refills between the MMA groups do not pay a DRAM round trip;
+ *   bits 4..7  resident CTAs per SM the K split aims at (0 = the default 5).
+ * Default 6 (measured best at M = 1, profiles/r02_ab_decode.jsonl).  Results are identical in every mode up to the
+ * order of the fp32 atomic adds across K slices. */
 int sb200_gptq4_set_decode(int mode);
 
 /* Tuning knob of the per-group tcgen05 kernel (impl 2): how its epilogue warps drain the accumulator out of tensor

@@ -21,6 +21,9 @@ dev = torch.device("cuda:0")
 SHAPES = [("qkvo", 4096, 4096, 4), ("gate_up", 4096, 11008, 2), ("down", 11008, 4096, 1)]  # name, K, N, count per layer
 LAYERS = 32
 TS_CHUNKS = [int(c) for c in os.environ.get("SB200_TS_CHUNKS", "512").split(",")]
+# the packed weights / scales / zeros of a loaded model are constants: the decode kernel may request them while the
+# previous linear is still draining (SB200_GPTQ4_STATIC_WEIGHTS, include/sparsebit_b200.h)
+STATIC = os.environ.get("SB200_STATIC_WEIGHTS", "1") == "1"
 
 
 def load_ref():
@@ -95,7 +98,7 @@ def run(ms, with_reference=True, quiet=False):
                 impls += [(f"ours_tcgen05_ts_c{c}", 3, c) for c in TS_CHUNKS]
             for label, impl, chunk in impls:
                 try:
-                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128, impl=impl, chunk_k=chunk),
+                    t = timeit(lambda i: ops.gptq4_matmul(x, *ws[i % copies][:1], y, *ws[i % copies][1:], 128, impl=impl, chunk_k=chunk, static_weights=STATIC),
                                20 if m > 64 else 200, copies)
                 except RuntimeError as e:
                     emit({"shape": name, "M": m, "impl": label, "error": str(e)[:100]})
@@ -124,10 +127,10 @@ def run(ms, with_reference=True, quiet=False):
 
             def layer(i):
                 q4, gu, dn = sets["qkvo"][4 * i:4 * i + 4], sets["gate_up"][2 * i:2 * i + 2], sets["down"][i]
-                ops.gptq4_matmul_batch([(xq, w[0], y, w[1], w[2]) for w, y in zip(q4[:3], ys["qkvo"][:3])], 128)
-                ops.gptq4_matmul(xq, q4[3][0], ys["qkvo"][3], q4[3][1], q4[3][2], 128)
-                ops.gptq4_matmul_batch([(xq, w[0], y, w[1], w[2]) for w, y in zip(gu, ys["gate_up"])], 128)
-                ops.gptq4_matmul(xd, dn[0], ys["down"][0], dn[1], dn[2], 128)
+                ops.gptq4_matmul_batch([(xq, w[0], y, w[1], w[2]) for w, y in zip(q4[:3], ys["qkvo"][:3])], 128, static_weights=STATIC)
+                ops.gptq4_matmul(xq, q4[3][0], ys["qkvo"][3], q4[3][1], q4[3][2], 128, static_weights=STATIC)
+                ops.gptq4_matmul_batch([(xq, w[0], y, w[1], w[2]) for w, y in zip(gu, ys["gate_up"])], 128, static_weights=STATIC)
+                ops.gptq4_matmul(xd, dn[0], ys["down"][0], dn[1], dn[2], 128, static_weights=STATIC)
 
             t = timeit(lambda i: layer(i % rounds), 60, rounds)
             emit({"shape": "layer(qkv|o|gate_up|down)", "M": m, "impl": "ours_fused_launches", "us": t * 1e6,

@@ -122,3 +122,58 @@ try:
     traffic()
 except Exception as e:
     print("traffic summary skipped:", e)
+
+
+def sweep_table(name="prof_all_kernels", log="gpurun_out/ncu_all.log"):
+    """One line per captured launch of the all-kernel sweep (scripts/exp/run_all_kernels.py), labelled with the operation
+    that launched it (the '## ...' markers of the run's log): duration, DRAM bytes and rate, issue-slot use, the two
+    largest stall reasons.  -> profiles/<tag>_prof_all_kernels_table.txt"""
+    import re
+
+    rows = list(csv.reader(raw_page(name).splitlines()))
+    while rows and "Kernel Name" not in rows[0]:
+        rows.pop(0)
+    hdr, units = rows[0], rows[1]
+    labels, cur = [], ""
+    for line in open(log, errors="replace"):
+        if line.startswith("## "):
+            cur = line[3:].strip()
+        elif line.startswith("==PROF== Profiling"):
+            labels.append(cur)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3,
+             "byte/second": 1.0, "Kbyte/second": 1e3, "Mbyte/second": 1e6, "Gbyte/second": 1e9, "Tbyte/second": 1e12}
+
+    def val(r, m, default=0.0):
+        if m not in hdr:
+            return default
+        i = hdr.index(m)
+        try:
+            return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        except ValueError:
+            return default
+
+    stalls = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+    out = [f"# all-kernel ncu sweep ({tag}): `ncu --metrics <scripts/ncu_metrics.txt> --clock-control none -k regex:sb200` over scripts/exp/run_all_kernels.py",
+           "# one line per captured launch, in launch order; times are single cold launches under the profiler (compare rates, not absolutes);",
+           "# DRAM GB/s = (dram__bytes_read + dram__bytes_write) / gpu__time_duration; pct = gpu__dram_throughput pct of peak; the full metric",
+           f"# list per launch is in {tag}_prof_all_kernels.txt", "",
+           f"{'operation':44s} {'kernel':40s} {'grid':>7s} {'regs':>4s} {'us':>9s} {'DRAM MB':>9s} {'GB/s':>7s} {'dram%':>6s} {'issue%':>6s} {'tensor%':>7s}  top stalls"]
+    for i, r in enumerate(rows[2:]):
+        kn = re.sub(r"^void |sb200::", "", r[hdr.index("Kernel Name")])
+        kn = re.sub(r"\((int|bool)\)", "", kn.split("(const")[0].split("(unsigned")[0].split("(sb200")[0].split("(DecBatch")[0])[:40]
+        us = val(r, "gpu__time_duration.sum")
+        mb = (val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / 1e6
+        st = sorted(((val(r, s), s.split("stalled_")[1].split("_per_issue")[0]) for s in stalls), reverse=True)[:2]
+        out.append(f"{(labels[i] if i < len(labels) else '')[:44]:44s} {kn:40s} {int(val(r, 'launch__grid_size')):7d} {int(val(r, 'launch__registers_per_thread')):4d} "
+                   f"{us:9.1f} {mb:9.2f} {mb / us * 1e3 if us else 0:7.0f} {val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):6.1f} "
+                   f"{val(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):6.1f} {val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):7.1f}  "
+                   + ", ".join(f"{n} {v:.1f}" for v, n in st))
+    open(f"profiles/{tag}_prof_all_kernels_table.txt", "w").write("\n".join(out) + "\n")
+    print("wrote", f"profiles/{tag}_prof_all_kernels_table.txt", len(rows) - 2, "launches")
+
+
+if "prof_all_kernels" in names:
+    try:
+        sweep_table()
+    except Exception as e:
+        print("sweep table skipped:", e)

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "sb200_mask_gt": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_minmax_qparams_multi": (c_int, [c_vp, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_matmul_batch": (c_int, [c_vp, c_int, c_i64, c_vp]),
+    "sb200_gptq4_matmul_batch_ex": (c_int, [c_vp, c_int, c_i64, c_int, c_vp]),
     "sb200_mask_rows_gt": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "sb200_mask_apply": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "sb200_mask_apply_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),

@@ -265,18 +265,34 @@ __global__ void __launch_bounds__(128) bwd_cols_kernel(const float* __restrict__
   }
 }
 
-__global__ void bwd_cols_finish_kernel(const double2* __restrict__ partial, int nblocks, int channels,
-                                       float* __restrict__ gs, float* __restrict__ gzp) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= channels) return;
-  double t0 = 0.0, t1 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    const double2 v = partial[(long long)b * channels + c];
-    t0 += v.x;
-    t1 += v.y;
+// gs[c] / gzp[c] = sum over the row blocks b of partial[b * channels + c], fixed order.  32 channels x 32 slices per
+// CTA: thread (s, c) sums the blocks b = s, s + 32, ... (two accumulators), the 32 slice sums of a channel are combined in
+// slice order.  (One thread per channel walking all ~600 row blocks serially took as long as the streaming pass itself.)
+__global__ void __launch_bounds__(1024) bwd_cols_finish_kernel(const double2* __restrict__ partial, int nblocks, int channels,
+                                                               float* __restrict__ gs, float* __restrict__ gzp) {
+  __shared__ double2 s_part[32][33];
+  const int lc = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lc;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  if (c < channels) {
+    int b = s;
+    for (; b + 32 < nblocks; b += 64) {
+      const double2 v = partial[(long long)b * channels + c], w = partial[(long long)(b + 32) * channels + c];
+      a0 += v.x; a1 += v.y; b0 += w.x; b1 += w.y;
+    }
+    if (b < nblocks) {
+      const double2 v = partial[(long long)b * channels + c];
+      a0 += v.x; a1 += v.y;
+    }
   }
-  if (gs) gs[c] = (float)t0;
-  if (gzp) gzp[c] = (float)t1;
+  s_part[s][lc] = make_double2(a0 + b0, a1 + b1);
+  __syncthreads();
+  if (s == 0 && c < channels) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int q = 0; q < 32; ++q) { t0 += s_part[q][lc].x; t1 += s_part[q][lc].y; }
+    if (gs) gs[c] = (float)t0;
+    if (gzp) gzp[c] = (float)t1;
+  }
 }
 
 static inline int persistent_grid(long long tiles, int ctas_per_sm) {
@@ -337,7 +353,7 @@ static int bwd_dispatch(const float* x, const float* scale, const float* zp, con
 #undef SB_GOC
     SB_LAUNCHED();
     if (need_red) {
-      bwd_cols_finish_kernel<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(partial, (int)nb, (int)channels, gs, gzp);
+      bwd_cols_finish_kernel<<<(unsigned)((channels + 31) / 32), 1024, 0, st>>>(partial, (int)nb, (int)channels, gs, gzp);
       SB_LAUNCHED();
     }
     return SB200_OK;

@@ -284,6 +284,21 @@ __device__ __forceinline__ void block_reduce_minmax(MinMaxAcc& a, float* sm) {
   }
   __syncthreads();
 }
+// Fixed-order finish of per-tile fp64 partials:  out[row * nval + k] += sum_j partial[(row * tpr + j) * nval + k].
+// One CTA per row; thread (s, k) = (tid / nval, tid % nval) sums the tiles j = s, s + S, s + 2S, ... (S = blockDim / nval
+// slices, four independent accumulators so that four loads are in flight), the S slice sums are combined in slice order
+// by thread k.  The association depends only on (tpr, blockDim), never on scheduling: run-to-run deterministic.
+// (The one-thread-per-output loops this replaces took 100 - 290 us for a single per-tensor row: a serial chain of
+// dependent-latency loads, longer than the streaming pass that produced the partials.)  Dynamic smem: S * nval doubles.
+__global__ void strided_finish_kernel(const double* __restrict__ partial, long long tpr, int nval, double* __restrict__ out);
+static inline int strided_finish_threads(long long tpr, int nval) {
+  long long slices = (tpr + 3) / 4;  // at least ~4 tiles per slice
+  if (slices < 1) slices = 1;
+  long long t = slices * nval;
+  if (t > 1024) t = (1024 / nval) * (long long)nval;
+  if (t < nval) t = nval;
+  return (int)((t + 31) / 32 * 32 > 1024 ? 1024 : (t + 31) / 32 * 32);
+}
 #endif  // __CUDACC__
 
 }  // namespace sb200

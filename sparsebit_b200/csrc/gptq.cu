@@ -12,7 +12,7 @@ int gptq4_simt(const float* x, const int32_t* qweight, float* out, const float* 
                long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
 bool gptq4_decode_supported(const int32_t* qweight, long long N);
 int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
-                 long long K, long long N, long long KW, int group_size, cudaStream_t st);
+                 long long K, long long N, long long KW, int group_size, int flags, cudaStream_t st);
 bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
                         long long KW, int group_size);
 size_t gptq4_tc_workspace(long long M, long long K, long long N, int group_size);
@@ -64,7 +64,7 @@ int sb200_gptq4_set_wait_backoff(int nanoseconds) {
 }
 
 int sb200_gptq4_set_decode(int mode) {
-  SB_REQUIRE(mode >= 0 && mode <= 3, "sb200_gptq4_set_decode: mode is a bit mask 0 .. 3 (bit 0 bulk-copy slab, bit 1 programmatic dependent launch; got %d)", mode);
+  SB_REQUIRE(mode >= 0 && mode <= 255, "sb200_gptq4_set_decode: mode is a bit mask 0 .. 255 (got %d)", mode);
   gptq4_decode_set_mode(mode);
   return SB200_OK;
 }
@@ -89,7 +89,7 @@ size_t sb200_gptq4_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_si
 
 static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                           int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size, int impl, int chunk_k,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+                          void* workspace, size_t workspace_bytes, void* stream, int flags = 0) {
   SB_REQUIRE(x && qweight && out && scales && zeros, "sb200_gptq4_matmul: null pointer argument");
   SB_REQUIRE(m > 0 && k > 0 && n > 0, "sb200_gptq4_matmul: empty operand (M=%lld K=%lld N=%lld)", (long long)m,
              (long long)k, (long long)n);
@@ -134,7 +134,7 @@ static int gptq4_dispatch(const float* x, const int32_t* qweight, float* out, co
   if (use == 2)
     return gptq4_tc(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, workspace, workspace_bytes, st);
   if (impl != 4 && gptq4_decode_supported(qweight, n))
-    return gptq4_decode(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
+    return gptq4_decode(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, flags, st);
   return gptq4_simt(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, st);
 }
 
@@ -148,9 +148,13 @@ int sb200_gptq4_matmul(const float* x, const int32_t* qweight, float* out, const
 int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                           int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size,
                           const sb200_gptq4_options* options, void* workspace, size_t workspace_bytes, void* stream) {
-  const int impl = options ? options->impl : 0, chunk_k = options ? options->chunk_k : 0;
+  const int impl = options ? options->impl : 0, chunk_k = options ? options->chunk_k : 0, flags = options ? options->flags : 0;
+  if (options) {
+    SB_REQUIRE((flags & ~SB200_GPTQ4_STATIC_WEIGHTS) == 0, "sb200_gptq4_matmul_ex: unknown flags 0x%x", flags);
+    for (int i = 0; i < 5; ++i) SB_REQUIRE(options->reserved[i] == 0, "sb200_gptq4_matmul_ex: reserved option fields must be zero");
+  }
   return gptq4_dispatch(x, qweight, out, scales, zeros, m, k, n, qweight_rows, group_size, impl, chunk_k, workspace,
-                        workspace_bytes, stream);
+                        workspace_bytes, stream, flags);
 }
 
 size_t sb200_gptq4_linear_f16_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size) {
@@ -189,7 +193,9 @@ int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_
   SB_LAUNCHED();
   bias_rows_kernel<<<ew_grid(m * n), 256, 0, st>>>(bias, y32, m, n);
   SB_LAUNCHED();
-  const int rc = gptq4_dispatch(x32, qweight, y32, scales, zeros, m, k, n, qweight_rows, group_size, 0, 0, rest, rest_bytes, stream);
+  // the kernel immediately in front is bias_rows_kernel (writes y32 only): the weight tables cannot be its output
+  const int rc = gptq4_dispatch(x32, qweight, y32, scales, zeros, m, k, n, qweight_rows, group_size, 0, 0, rest, rest_bytes, stream,
+                                SB200_GPTQ4_STATIC_WEIGHTS);
   if (rc) return rc;
   f32_to_f16_kernel<<<ew_grid(m * n), 256, 0, st>>>(y32, yh, m * n);
   SB_LAUNCHED();

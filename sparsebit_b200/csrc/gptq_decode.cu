@@ -81,10 +81,12 @@ struct DecBatch {
 //   SLAB: the packed-weight slab [blocks_per_slice][16][544 B] comes first, and only x_rows = min(M, 8 NB) token rows
 //   are allocated for xh / xl / xsum (MMA token columns beyond the real tokens re-read the last real row; their results
 //   are never written back).
-// pdl: launched with programmatic stream serialisation -- the next kernel of the stream may start while this one runs
-// (griddepcontrol.launch_dependents) and this one touches nothing a predecessor may still be writing (the activations,
-// `out`) before griddepcontrol.wait; the packed weights, scales and zeros are constants of the model and are requested
-// before the wait, so their DRAM latency overlaps the tail of the previous linear.
+// pdl (bit mask): bit 0 = launched with programmatic stream serialisation: the next kernel of the stream may start
+// while this one runs (griddepcontrol.launch_dependents at the top) and this kernel executes griddepcontrol.wait before
+// it touches global memory -- plain stream semantics, but the launch latency and CTA ramp-up overlap the predecessor's
+// tail.  bit 2 = the caller declared the packed weights, scales and zeros constants of the model (not produced by the
+// kernel immediately in front on the stream): they are requested BEFORE the wait, so their DRAM latency overlaps the
+// tail of the previous linear too; only the activations and `out` are behind the wait.  bit 1 = L2 prefetch (below).
 template <int NB, bool SLAB>
 __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_constant__ DecBatch batch, int M,
                                                                  int blocks_per_slice, int x_rows, int pdl) {
@@ -136,11 +138,12 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
   };
 
   uint4 wa[4], wb[4];
+  if (pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if ((pdl & 5) == 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // strict: nothing is read before the predecessor is done
   if (SLAB) {
     if (tid < nb) mbar_init(&s_bar[tid], kDecBlockK / 8);  // every row thread of a block arrives exactly once
     mbar_fence_init();
     __syncthreads();
-    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int bl = tid >> 4, r = tid & 15;
     if (bl < nb) {
       const int row = (b0 + bl) * (kDecBlockK / 8) + r;
@@ -156,9 +159,24 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       }
     }
   } else {
-    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     load_group(0, wa);
     if (nb > 1) load_group(1, wb);
+    if (pdl & 2) {
+      // The register file holds two 128-K blocks per lane; the blocks after them are requested into L2 right away
+      // (one prefetch per 128-byte line: a warp's LDG.128 covers four lines, lanes g == 0 own one each), so that every
+      // byte of the CTA's slice is on its way from DRAM before the activations are staged and the refills between the
+      // MMA groups hit L2 instead of paying a DRAM round trip in the middle of the CTA's short life.
+      if (g == 0 && col_ok) {
+        for (int bl = 2; bl < nb; ++bl) {
+          const int row0 = (b0 + bl) * (kDecBlockK / 8) + c;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int row = row0 + 4 * ch;
+            if (row < KW) asm volatile("prefetch.global.L2 [%0];" ::"l"(qw + (size_t)row * N + nbase));
+          }
+        }
+      }
+    }
   }
 
   // scales / zeros of this CTA's 128 features for every 128-K block of its slice: thread = feature, so the table is
@@ -174,8 +192,8 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     }
   }
 
-  // everything above reads constants of the model; from here on the activations and `out` of this call are touched
-  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // static-weights form: everything above read constants of the model; from here on the activations and `out` are touched
+  if ((pdl & 5) == 5) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   for (int m0 = 0; m0 < M; m0 += MT) {
     // The kernel lives for a few microseconds, i.e. a handful of DRAM latencies: the packed weights (the whole slab,
@@ -341,13 +359,15 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
 bool gptq4_decode_supported(const int32_t* qweight, long long N) { return (N % 4 == 0) && aligned16(qweight); }
 
 // Decode-kernel variant (process-wide benchmarking / test switch, sb200_gptq4_set_decode): bit 0 = bulk-copy weight
-// slab (SLAB), bit 1 = programmatic dependent launch.
-static int g_dec_mode = 3;
+// slab (SLAB), bit 1 = programmatic dependent launch, bit 2 = L2 prefetch of the 128-K blocks beyond the two held in
+// registers (register-staged variant only), bit 3 = treat every call as SB200_GPTQ4_STATIC_WEIGHTS,
+// bits 4..7 = resident CTAs per SM the K split aims at (0 = 5).
+static int g_dec_mode = 6;
 void gptq4_decode_set_mode(int mode) { g_dec_mode = mode; }
 int gptq4_decode_get_mode() { return g_dec_mode; }
 
 template <int NB, bool SLAB>
-static int dec_launch(const DecBatch& batch, dim3 grid, size_t smem, int M, int S, int x_rows, bool pdl, cudaStream_t st) {
+static int dec_launch(const DecBatch& batch, dim3 grid, size_t smem, int M, int S, int x_rows, bool pdl, int kflags, cudaStream_t st) {
   static std::atomic<int> attr_done[64];
   if (smem > 48 * 1024) SB_CUDA(ensure_dyn_smem(gptq4_decode_kernel<NB, SLAB>, (int)smem, attr_done));
   cudaLaunchConfig_t cfg = {};
@@ -360,13 +380,13 @@ static int dec_launch(const DecBatch& batch, dim3 grid, size_t smem, int M, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  SB_CUDA(cudaLaunchKernelEx(&cfg, gptq4_decode_kernel<NB, SLAB>, batch, M, S, x_rows, pdl ? 1 : 0));
+  SB_CUDA(cudaLaunchKernelEx(&cfg, gptq4_decode_kernel<NB, SLAB>, batch, M, S, x_rows, kflags));
   SB_LAUNCHED();
   return SB200_OK;
 }
 
 // `count` problems sharing M in one launch (count == 1: the plain entry point)
-int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStream_t st) {
+int gptq4_decode_batch(const DecProblem* probs, int count, long long M, int flags, cudaStream_t st) {
   DecBatch batch;
   batch.count = count;
   int colblocks = 0, nblk_max = 0;
@@ -379,10 +399,13 @@ int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStre
   }
   for (int i = count; i < kDecMaxProblems; ++i) batch.p[i] = batch.p[0];
   const int nbk = M <= 8 ? 1 : (M <= 16 ? 2 : 4);
-  const bool slab = (g_dec_mode & 1) != 0, pdl = (g_dec_mode & 2) != 0;
+  const bool slab = (g_dec_mode & 1) != 0, pdl = (g_dec_mode & 2) != 0, prefetch = (g_dec_mode & 4) != 0;
+  const bool static_w = (g_dec_mode & 8) != 0 || (flags & SB200_GPTQ4_STATIC_WEIGHTS) != 0;
+  const int kflags = (pdl ? 1 : 0) | (prefetch ? 2 : 0) | (static_w ? 4 : 0);
+  const int per_sm = ((g_dec_mode >> 4) & 15) ? ((g_dec_mode >> 4) & 15) : 5;
   // K slices: ~5 CTAs per SM (what the register file holds: 4 warps x 96 registers), each streaming as long a K
   // range as that allows, bounded by the activation slice held in shared memory
-  int want = (sm_count() * 5 + colblocks - 1) / colblocks;
+  int want = (sm_count() * per_sm + colblocks - 1) / colblocks;
   if (want < 1) want = 1;
   if (want > nblk_max) want = nblk_max;
   int S = (nblk_max + want - 1) / want;
@@ -394,8 +417,8 @@ int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStre
   const int x_rows = slab ? (int)(M < mt ? M : mt) : mt;
   const size_t smem = (slab ? (size_t)S * kSlabGroupBytes : 0) + (size_t)2 * x_rows * (S * kDecBlockK + 32) * sizeof(__half) +
                       (size_t)x_rows * S * sizeof(float) + (size_t)mt * sizeof(float) + (size_t)2 * S * kDecCols * sizeof(float);
-#define SB_GO(NB_) (slab ? dec_launch<NB_, true>(batch, grid, smem, (int)M, S, x_rows, pdl, st) \
-                         : dec_launch<NB_, false>(batch, grid, smem, (int)M, S, x_rows, pdl, st))
+#define SB_GO(NB_) (slab ? dec_launch<NB_, true>(batch, grid, smem, (int)M, S, x_rows, pdl, kflags, st) \
+                         : dec_launch<NB_, false>(batch, grid, smem, (int)M, S, x_rows, pdl, kflags, st))
   if (nbk == 1) return SB_GO(1);
   if (nbk == 2) return SB_GO(2);
   return SB_GO(4);
@@ -403,7 +426,7 @@ int gptq4_decode_batch(const DecProblem* probs, int count, long long M, cudaStre
 }
 
 int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
-                 long long K, long long N, long long KW, int group_size, cudaStream_t st) {
+                 long long K, long long N, long long KW, int group_size, int flags, cudaStream_t st) {
   DecProblem p;
   p.x = x;
   p.qw = reinterpret_cast<const uint32_t*>(qweight);
@@ -416,14 +439,19 @@ int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float
   p.G = (int)((K + group_size - 1) / group_size);
   p.group_size = group_size;
   p.colblock_begin = 0;
-  return gptq4_decode_batch(&p, 1, M, st);
+  return gptq4_decode_batch(&p, 1, M, flags, st);
 }
 
 }  // namespace sb200
 
 using namespace sb200;
 
+extern "C" int sb200_gptq4_matmul_batch_ex(const sb200_gptq4_problem* problems, int count, int64_t m, int flags, void* stream);
 extern "C" int sb200_gptq4_matmul_batch(const sb200_gptq4_problem* problems, int count, int64_t m, void* stream) {
+  return sb200_gptq4_matmul_batch_ex(problems, count, m, 0, stream);
+}
+extern "C" int sb200_gptq4_matmul_batch_ex(const sb200_gptq4_problem* problems, int count, int64_t m, int flags, void* stream) {
+  SB_REQUIRE((flags & ~SB200_GPTQ4_STATIC_WEIGHTS) == 0, "sb200_gptq4_matmul_batch_ex: unknown flags 0x%x", flags);
   SB_REQUIRE(problems && count >= 1 && count <= kDecMaxProblems, "sb200_gptq4_matmul_batch: 1 .. %d problems (got %d)", kDecMaxProblems, count);
   SB_REQUIRE(m >= 1 && m <= 32, "sb200_gptq4_matmul_batch: decode-sized M only (1 .. 32, got %lld)", (long long)m);
   DecProblem p[kDecMaxProblems];
@@ -448,5 +476,5 @@ extern "C" int sb200_gptq4_matmul_batch(const sb200_gptq4_problem* problems, int
     p[i].group_size = gs;
     p[i].colblock_begin = 0;
   }
-  return gptq4_decode_batch(p, count, m, (cudaStream_t)stream);
+  return gptq4_decode_batch(p, count, m, flags, (cudaStream_t)stream);
 }

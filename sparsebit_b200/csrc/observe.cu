@@ -194,10 +194,12 @@ __global__ void __launch_bounds__(kThreads) hist_kernel(const float* __restrict_
     const long long nv = n >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     long long i = gt;
-    for (; i + T < nv; i += 2 * T) {
-      const float4 a = ld_stream4(x4 + i), b = ld_stream4(x4 + i + T);
+    for (; i + 3 * T < nv; i += 4 * T) {  // four independent 128-bit loads in flight per thread
+      const float4 a = ld_stream4(x4 + i), b = ld_stream4(x4 + i + T), c = ld_stream4(x4 + i + 2 * T), d = ld_stream4(x4 + i + 3 * T);
       add(a.x); add(a.y); add(a.z); add(a.w);
       add(b.x); add(b.y); add(b.z); add(b.w);
+      add(c.x); add(c.y); add(c.z); add(c.w);
+      add(d.x); add(d.y); add(d.z); add(d.w);
     }
     for (; i < nv; i += T) {
       const float4 a = ld_stream4(x4 + i);
@@ -311,22 +313,14 @@ __global__ void __launch_bounds__(kThreads) mse_sweep_kernel(const float* __rest
   }
 }
 
-// sse[row*ncand + i] += sum_j partial[(row*tpr + j)*ncand + i]   (fixed order)
-__global__ void mse_finish_kernel(const double* __restrict__ partial, long long rows, long long tpr, int ncand,
-                                  double* __restrict__ sse) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * ncand) return;
-  const long long row = idx / ncand;
-  const int i = (int)(idx - row * ncand);
-  double t = 0.0;
-  for (long long j = 0; j < tpr; ++j) t += partial[(row * tpr + j) * ncand + i];
-  sse[idx] += t;
-}
+// sse[row*ncand + i] += sum_j partial[(row*tpr + j)*ncand + i]   (fixed order): strided_finish_kernel below
 
 // =========================================================================================
 // Radix select (3 passes: 11 + 11 + 10 key bits) and sign counting
 // =========================================================================================
-constexpr long long kSelSeg = 65536;  // elements per (row, segment) tile
+// elements per (row, segment) tile.  (65536 until r02: a 19 M-element tensor then made 296 CTAs, two per SM with two
+// LDG.128 per thread in flight -- 16 KB per SM, a quarter of what the HBM pipe needs; every pass ran at 2 TB/s.)
+constexpr long long kSelSeg = 16384;
 constexpr int kSelMaxTargets = 2;
 constexpr int kSelCopies = 4;  // pass-0 sub-histograms per CTA (spreads hot exponent buckets)
 
@@ -382,10 +376,13 @@ __global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __re
     const float4* q = reinterpret_cast<const float4*>(p + head);
     const long long nv = (len - head) >> 2;
     long long i = threadIdx.x;
-    for (; i + blockDim.x < nv; i += 2 * blockDim.x) {
-      const float4 a = ld_stream4(q + i), b = ld_stream4(q + i + blockDim.x);
+    for (; i + 3LL * blockDim.x < nv; i += 4LL * blockDim.x) {  // four independent 128-bit loads in flight per thread
+      const float4 a = ld_stream4(q + i), b = ld_stream4(q + i + blockDim.x), c = ld_stream4(q + i + 2LL * blockDim.x),
+                   d = ld_stream4(q + i + 3LL * blockDim.x);
       add(a.x); add(a.y); add(a.z); add(a.w);
       add(b.x); add(b.y); add(b.z); add(b.w);
+      add(c.x); add(c.y); add(c.z); add(c.w);
+      add(d.x); add(d.y); add(d.z); add(d.w);
     }
     for (; i < nv; i += blockDim.x) {
       const float4 a = ld_stream4(q + i);
@@ -615,15 +612,28 @@ __global__ void __launch_bounds__(kThreads) moments_tile_kernel(const float* __r
   }
 }
 
-__global__ void moments_finish_kernel(const double* __restrict__ partial, long long rows, long long tpr,
-                                      double* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * kMomVals) return;
-  const long long row = i / kMomVals;
-  const int k = (int)(i - row * kMomVals);
-  double t = 0;
-  for (long long j = 0; j < tpr; ++j) t += partial[(row * tpr + j) * kMomVals + k];
-  out[i] += t;
+__global__ void strided_finish_kernel(const double* __restrict__ partial, long long tpr, int nval, double* __restrict__ out) {
+  extern __shared__ double s_fin[];  // [S][nval]
+  const int S = blockDim.x / nval;
+  const int s = threadIdx.x / nval, k = threadIdx.x - s * nval;
+  const long long row = blockIdx.x;
+  if (s < S) {
+    const double* base = partial + row * tpr * nval + k;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    long long j = s;
+    for (; j + 3LL * S < tpr; j += 4LL * S) {
+      const double v0 = base[j * nval], v1 = base[(j + S) * nval], v2 = base[(j + 2LL * S) * nval], v3 = base[(j + 3LL * S) * nval];
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; j < tpr; j += S) a0 += base[j * nval];
+    s_fin[s * nval + k] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (threadIdx.x < nval) {
+    double t = 0.0;
+    for (int q = 0; q < S; ++q) t += s_fin[q * nval + threadIdx.x];
+    out[row * nval + threadIdx.x] += t;
+  }
 }
 
 }  // namespace sb200
@@ -675,8 +685,8 @@ int sb200_observe_hist(const float* x, int64_t n, const float* range, int bins, 
   SB_REQUIRE(n > 0, "sb200_observe_hist: empty tensor");
   SB_REQUIRE(bins > 0 && bins <= 8192, "sb200_observe_hist: bins must be in [1, 8192] (got %d)", bins);
   const size_t smem = (size_t)bins * 4;
-  const long long blocks = (n / 4 + kThreads * 2 - 1) / (kThreads * 2);
-  hist_kernel<<<persistent_grid(blocks, 4), kThreads, smem, (cudaStream_t)stream>>>(
+  const long long blocks = (n / 4 + kThreads * 4 - 1) / (kThreads * 4);
+  hist_kernel<<<persistent_grid(blocks, 8), kThreads, smem, (cudaStream_t)stream>>>(
       x, n, range, bins, reinterpret_cast<unsigned long long*>(counts));
   SB_LAUNCHED();
   return SB200_OK;
@@ -706,7 +716,10 @@ int sb200_observe_mse_sweep(const float* x, int64_t rows, int64_t row_len, const
                                                                     (float)qmin, (float)qmax, (double*)workspace);
   SB_LAUNCHED();
   const long long outn = rows * ncand;
-  mse_finish_kernel<<<(unsigned)((outn + 127) / 128), 128, 0, st>>>((const double*)workspace, rows, tpr, ncand, sse);
+  {
+    const int ft = strided_finish_threads(tpr, ncand);
+    strided_finish_kernel<<<(unsigned)rows, ft, (size_t)(ft / ncand) * ncand * sizeof(double), st>>>((const double*)workspace, tpr, ncand, sse);
+  }
   SB_LAUNCHED();
   return SB200_OK;
 }
@@ -735,7 +748,7 @@ int sb200_select_hist_counts(const float* x, int64_t rows, int64_t row_len, int 
   SB_REQUIRE(pass >= 0 && pass <= 2, "sb200_select_hist: pass must be 0, 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
   const long long tiles = rows * ((row_len + kSelSeg - 1) / kSelSeg);
-  const int grid = persistent_grid(tiles, 4);
+  const int grid = persistent_grid(tiles, 6);  // pass 0 holds 32 KB of sub-histograms per CTA: 6 fit next to each other
   auto* sl = reinterpret_cast<const unsigned long long*>(sel);
   auto* hs = reinterpret_cast<unsigned long long*>(hist);
   auto* sc = reinterpret_cast<unsigned long long*>(sign_counts);
@@ -806,7 +819,10 @@ int sb200_observe_moments(const float* x, int64_t rows, int64_t row_len, const d
   moments_tile_kernel<<<persistent_grid(tiles, 8), kThreads, 0, (cudaStream_t)stream>>>(x, rows, row_len, centre, partial);
   SB_LAUNCHED();
   const long long n = rows * kMomVals;
-  moments_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partial, rows, tpr, out);
+  {
+    const int ft = strided_finish_threads(tpr, kMomVals);
+    strided_finish_kernel<<<(unsigned)rows, ft, (size_t)(ft / kMomVals) * kMomVals * sizeof(double), (cudaStream_t)stream>>>(partial, tpr, kMomVals, out);
+  }
   SB_LAUNCHED();
   return SB200_OK;
 }

@@ -516,12 +516,17 @@ _gptq_ws = {}
 
 
 class _Gptq4Options(ctypes.Structure):  # include/sparsebit_b200.h sb200_gptq4_options
-    _fields_ = [("impl", ctypes.c_int), ("chunk_k", ctypes.c_int), ("reserved", ctypes.c_int * 6)]
+    _fields_ = [("impl", ctypes.c_int), ("chunk_k", ctypes.c_int), ("flags", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
 
 
-def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0, impl=None, chunk_k=0):
+GPTQ4_STATIC_WEIGHTS = 1  # include/sparsebit_b200.h SB200_GPTQ4_STATIC_WEIGHTS
+
+
+def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0, impl=None, chunk_k=0, static_weights=False):
     """In-place ``out += x @ dequant(qweight)`` (vecquant4matmul contract, cuda_kernel.cpp:10-23).
-    ``impl`` / ``chunk_k``: per-call kernel selection (sb200_gptq4_matmul_ex); None = the library default."""
+    ``impl`` / ``chunk_k``: per-call kernel selection (sb200_gptq4_matmul_ex); None = the library default.
+    ``static_weights``: qweight / scales / zeros are constants of the model (not written by the kernel just in front on
+    the stream), so the decode kernel may fetch them while its predecessor is still draining."""
     lib = _lib.load()
     _req(x, "inp1"), _req(out, "out"), _req(scales, "scales"), _req(zeros, "zeros")
     _req(qweight, "inp2", torch.int32)
@@ -543,12 +548,12 @@ def gptq4_matmul(x, qweight, out, scales, zeros, group_size=0, impl=None, chunk_
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             _gptq_ws[key] = ws
     with torch.cuda.device(x.device):
-        if impl is None and not chunk_k:
+        if impl is None and not chunk_k and not static_weights:
             check(lib.sb200_gptq4_matmul(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(), zeros.data_ptr(),
                                          m, k, n, qweight.shape[0], int(group_size), ws.data_ptr() if ws is not None else None,
                                          ws_bytes, _stream(x)))
         else:
-            opts = _Gptq4Options(int(impl or 0), int(chunk_k))
+            opts = _Gptq4Options(int(impl or 0), int(chunk_k), GPTQ4_STATIC_WEIGHTS if static_weights else 0)
             check(lib.sb200_gptq4_matmul_ex(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), scales.data_ptr(),
                                             zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size), ctypes.byref(opts),
                                             ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x)))
@@ -561,9 +566,9 @@ class _Gptq4Problem(ctypes.Structure):  # include/sparsebit_b200.h sb200_gptq4_p
                 ("group_size", ctypes.c_int)]
 
 
-def gptq4_matmul_batch(problems, group_size=0):
+def gptq4_matmul_batch(problems, group_size=0, static_weights=False):
     """Up to 4 decode-sized linears sharing M in ONE launch (q / k / v, gate / up): ``problems`` = [(x, qweight, out, scales,
-    zeros)], every ``out`` pre-initialised and accumulated in place (sb200_gptq4_matmul_batch)."""
+    zeros)], every ``out`` pre-initialised and accumulated in place (sb200_gptq4_matmul_batch[_ex])."""
     lib = _lib.load()
     m = None
     arr = (_Gptq4Problem * len(problems))()
@@ -581,7 +586,8 @@ def gptq4_matmul_batch(problems, group_size=0):
                                int(group_size))
     dev = problems[0][0].device
     with torch.cuda.device(dev):
-        check(lib.sb200_gptq4_matmul_batch(arr, len(problems), m, torch.cuda.current_stream(dev).cuda_stream))
+        check(lib.sb200_gptq4_matmul_batch_ex(arr, len(problems), m, GPTQ4_STATIC_WEIGHTS if static_weights else 0,
+                                              torch.cuda.current_stream(dev).cuda_stream))
     return [p[2] for p in problems]
 
 

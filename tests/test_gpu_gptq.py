@@ -120,17 +120,19 @@ DECODE_CASES = [(1, 4096, 4096, 128), (8, 1024, 512, 128), (9, 1024, 260, 128), 
 
 @pytest.fixture
 def decode_mode():
-    """sb200_gptq4_set_decode is process-wide: restore the default (3 = bulk-copy slab + programmatic launch) afterwards."""
+    """sb200_gptq4_set_decode is process-wide: restore the default (6 = programmatic dependent launch + L2 prefetch) afterwards.
+    Bits: 1 bulk-copy weight slab, 2 programmatic launch, 4 L2 prefetch of the later K blocks, 8 every call counts as
+    SB200_GPTQ4_STATIC_WEIGHTS (weights requested before griddepcontrol.wait), high nibble CTAs per SM."""
     from sparsebit_b200 import _lib
 
     lib = _lib.load()
     yield lambda mode: _lib.check(lib.sb200_gptq4_set_decode(mode))
-    _lib.check(lib.sb200_gptq4_set_decode(3))
+    _lib.check(lib.sb200_gptq4_set_decode(6))
 
 
 @pytest.mark.parametrize("m,k,n,gs", DECODE_CASES)
 @pytest.mark.parametrize("fp16_acts", [False, True])
-@pytest.mark.parametrize("mode", [3, 1, 0])  # slab + PDL (default), slab alone, register-staged LDG.128 variant
+@pytest.mark.parametrize("mode", [6, 14, 11, 0x82])  # default; + static weights; slab variant; 8 CTAs per SM, no prefetch
 def test_decode_hmma_path_vs_fp64_oracle(m, k, n, gs, fp16_acts, mode, decode_mode):
     decode_mode(mode)
     rng = np.random.default_rng(13 * k + n + m)
@@ -367,7 +369,7 @@ def test_layer_streaming_equals_resident_execution():
     assert all(m.qweight.numel() == 0 for b in blocks for m in b.modules() if isinstance(m, QuantLinear))
 
 
-@pytest.mark.parametrize("mode", [3, 2, 0])
+@pytest.mark.parametrize("mode", [6, 14, 11, 0])
 @pytest.mark.parametrize("graph", [False, True])
 def test_decode_chain_of_dependent_linears_under_programmatic_launch(mode, graph, decode_mode):
     """y1 = W1 x, y2 = W2 y1, y3 = W3 y2 launched back to back on one stream: with programmatic dependent launch a
@@ -391,7 +393,7 @@ def test_decode_chain_of_dependent_linears_under_programmatic_launch(mode, graph
             y.zero_()
         cur = xin
         for (qw, sc, zr, *_), y in zip(layers, ys):  # three decode kernels back to back, each reading its predecessor's out
-            ops.gptq4_matmul(cur, qw, y, sc, zr, 128, impl=1)
+            ops.gptq4_matmul(cur, qw, y, sc, zr, 128, impl=1, static_weights=(mode == 6 and graph))  # also the per-call flag
             cur = y
 
     xt = t(x)
