@@ -318,9 +318,10 @@ __global__ void __launch_bounds__(kThreads) mse_sweep_kernel(const float* __rest
 // =========================================================================================
 // Radix select (3 passes: 11 + 11 + 10 key bits) and sign counting
 // =========================================================================================
-// elements per (row, segment) tile.  (65536 until r02: a 19 M-element tensor then made 296 CTAs, two per SM with two
-// LDG.128 per thread in flight -- 16 KB per SM, a quarter of what the HBM pipe needs; every pass ran at 2 TB/s.)
-constexpr long long kSelSeg = 16384;
+// Elements per (row, segment) tile, chosen per call (sel_seg): 65536 when that still gives every SM several CTAs, halved
+// down to 16384 otherwise.  (A fixed 65536 made 296 CTAs out of a 19 M-element tensor -- two per SM, 16 KB of loads in
+// flight per SM, every pass at 2 TB/s; a fixed 16384 costs large tensors 10 % in per-tile histogram flushes.)
+constexpr long long kSelSegMax = 65536, kSelSegMin = 16384;
 constexpr int kSelMaxTargets = 2;
 constexpr int kSelCopies = 4;  // pass-0 sub-histograms per CTA (spreads hot exponent buckets)
 
@@ -335,21 +336,21 @@ __device__ __forceinline__ int pass_bits(int pass) { return pass == 2 ? 10 : 11;
 // [2] final key, [3] reserved.
 template <int PASS>
 __global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __restrict__ x, long long rows,
-                                                               long long row_len, int ntpr,
+                                                               long long row_len, long long seg, int ntpr,
                                                                const unsigned long long* __restrict__ sel,
                                                                unsigned long long* __restrict__ hist, int key_mode,
                                                                unsigned long long* __restrict__ sign_counts) {
   extern __shared__ unsigned int s_hist[];  // PASS 0: kSelCopies * 2048 ; else ntpr * 2048
   const int nslots = (PASS == 0) ? kSelCopies : ntpr;
-  const long long spr = (row_len + kSelSeg - 1) / kSelSeg;
+  const long long spr = (row_len + seg - 1) / seg;
   const long long total = rows * spr;
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < nslots * SB200_SELECT_BINS; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const long long row = tile / spr, j = tile - row * spr;
-    const long long off = j * kSelSeg;
-    const long long len = (row_len - off) < kSelSeg ? (row_len - off) : kSelSeg;
+    const long long off = j * seg;
+    const long long len = (row_len - off) < seg ? (row_len - off) : seg;
     const float* p = x + row * row_len + off;
     uint32_t pre[kSelMaxTargets] = {0, 0};
     if (PASS > 0) {
@@ -528,15 +529,15 @@ __global__ void percentile_ranks_kernel(const unsigned long long* __restrict__ c
   sel[(r * 2 + 1) * SB200_SELECT_STATE_WORDS + 1] = (unsigned long long)(kmax - 1);
 }
 
-__global__ void count_sign_kernel(const float* __restrict__ x, long long rows, long long row_len,
+__global__ void count_sign_kernel(const float* __restrict__ x, long long rows, long long row_len, long long seg,
                                   unsigned long long* __restrict__ counts) {
-  const long long spr = (row_len + kSelSeg - 1) / kSelSeg;
+  const long long spr = (row_len + seg - 1) / seg;
   const long long total = rows * spr;
   const int lane = threadIdx.x & 31;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const long long row = tile / spr, j = tile - row * spr;
-    const long long off = j * kSelSeg;
-    const long long len = (row_len - off) < kSelSeg ? (row_len - off) : kSelSeg;
+    const long long off = j * seg;
+    const long long len = (row_len - off) < seg ? (row_len - off) : seg;
     const float* p = x + row * row_len + off;
     unsigned int neg = 0, pos = 0;
     for (long long i = threadIdx.x; i < len; i += blockDim.x) {
@@ -557,6 +558,12 @@ static inline int persistent_grid(long long tiles, int ctas_per_sm) {
   long long cap = (long long)sm_count() * ctas_per_sm;
   if (tiles < 1) tiles = 1;
   return (int)(tiles < cap ? tiles : cap);
+}
+static inline long long sel_seg(long long rows, long long row_len) {
+  long long seg = kSelSegMax;
+  const long long want = (long long)sm_count() * 6;
+  while (seg > kSelSegMin && rows * ((row_len + seg - 1) / seg) < want) seg >>= 1;
+  return seg;
 }
 
 
@@ -747,20 +754,21 @@ int sb200_select_hist_counts(const float* x, int64_t rows, int64_t row_len, int 
              "sb200_select_hist: ntargets_per_row must be 1 or 2 (got %d)", ntargets_per_row);
   SB_REQUIRE(pass >= 0 && pass <= 2, "sb200_select_hist: pass must be 0, 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long tiles = rows * ((row_len + kSelSeg - 1) / kSelSeg);
+  const long long seg = sel_seg(rows, row_len);
+  const long long tiles = rows * ((row_len + seg - 1) / seg);
   const int grid = persistent_grid(tiles, 6);  // pass 0 holds 32 KB of sub-histograms per CTA: 6 fit next to each other
   auto* sl = reinterpret_cast<const unsigned long long*>(sel);
   auto* hs = reinterpret_cast<unsigned long long*>(hist);
   auto* sc = reinterpret_cast<unsigned long long*>(sign_counts);
   if (pass == 0) {
     const size_t smem = (size_t)kSelCopies * SB200_SELECT_BINS * 4;
-    select_hist_kernel<0><<<grid, kThreads, smem, st>>>(x, rows, row_len, ntargets_per_row, sl, hs, key_mode, sc);
+    select_hist_kernel<0><<<grid, kThreads, smem, st>>>(x, rows, row_len, seg, ntargets_per_row, sl, hs, key_mode, sc);
   } else {
     const size_t smem = (size_t)ntargets_per_row * SB200_SELECT_BINS * 4;
     if (pass == 1)
-      select_hist_kernel<1><<<grid, kThreads, smem, st>>>(x, rows, row_len, ntargets_per_row, sl, hs, key_mode, nullptr);
+      select_hist_kernel<1><<<grid, kThreads, smem, st>>>(x, rows, row_len, seg, ntargets_per_row, sl, hs, key_mode, nullptr);
     else
-      select_hist_kernel<2><<<grid, kThreads, smem, st>>>(x, rows, row_len, ntargets_per_row, sl, hs, key_mode, nullptr);
+      select_hist_kernel<2><<<grid, kThreads, smem, st>>>(x, rows, row_len, seg, ntargets_per_row, sl, hs, key_mode, nullptr);
   }
   SB_LAUNCHED();
   return SB200_OK;
@@ -787,9 +795,10 @@ int sb200_select_read(const uint64_t* sel, int64_t ntargets_total, int key_mode,
 int sb200_count_sign(const float* x, int64_t rows, int64_t row_len, int64_t* counts, void* stream) {
   SB_REQUIRE(x && counts, "sb200_count_sign: null pointer argument");
   SB_REQUIRE(rows > 0 && row_len > 0, "sb200_count_sign: empty tensor");
-  const long long tiles = rows * ((row_len + kSelSeg - 1) / kSelSeg);
+  const long long seg = sel_seg(rows, row_len);
+  const long long tiles = rows * ((row_len + seg - 1) / seg);
   count_sign_kernel<<<persistent_grid(tiles, 8), kThreads, 0, (cudaStream_t)stream>>>(
-      x, rows, row_len, (unsigned long long*)counts);
+      x, rows, row_len, seg, (unsigned long long*)counts);
   SB_LAUNCHED();
   return SB200_OK;
 }
