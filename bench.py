@@ -895,6 +895,12 @@ def main():
                                                  "fp32-level accuracy, so the tensor pipe does 2x this work"},
                     "roofline_decode": {"bound": "hbm", "achieved": dec_bytes / t_dec / 1e9, "peak": peak, "unit": "GB/s",
                                         "frac": dec_bytes / t_dec / 1e9 / peak, "algorithmic_bytes_per_token": dec_bytes}}
+            try:  # the model path: QuantLinear.forward with fp16 activations (sb200_gptq4_linear_f16_ex), one launch per linear
+                f16 = bench_gptq.run_f16_linear(1)
+                gptq["decode_f16_linear"] = {"tok_s_one_launch": 1.0 / f16["one_launch"], "tok_s_staged_four_launches": 1.0 / f16["staged"],
+                                             "api": "ops.gptq4_linear_f16 (QuantLinear.forward, fp16 in / out incl. bias), one launch per linear"}
+            except Exception as e:
+                gptq["decode_f16_linear"] = {"error": repr(e)[:160]}
             # end to end through ops.gptq4_matmul with HOST activations: one decoder layer's 7 linears (x from pinned host
             # memory, result read back), scaled to the 32 layers
             try:

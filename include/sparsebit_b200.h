@@ -379,6 +379,17 @@ int sb200_gptq4_matmul_batch_ex(const sb200_gptq4_problem* problems, int count, 
  * smaller M is staged through fp32 inside the library.  Same accuracy as the fp32 entry point before the final
  * rounding to fp16.  workspace: sb200_gptq4_linear_f16_workspace_bytes(...) bytes. */
 size_t sb200_gptq4_linear_f16_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size);
+/* Decode-sized M (<= 32) in ONE launch: the decode kernel reads the fp16 activations itself, every K-slice CTA stores its
+ * fp32 partial sums into its own slot of the workspace and the last slice CTA of a 128-feature block to arrive adds the
+ * slots in slice order, adds the bias and writes fp16 (deterministic; no cast / bias / cast launches around the kernel).
+ * `state`: sb200_gptq4_linear_f16_state_bytes() bytes of device memory, ZERO-INITIALISED ONCE by the caller and then
+ * left alone (the kernel returns its arrival counters to zero); one state + workspace pair serves one stream at a
+ * time.  state == NULL (or M > 32) falls back to sb200_gptq4_linear_f16's staging.  flags: SB200_GPTQ4_STATIC_WEIGHTS. */
+size_t sb200_gptq4_linear_f16_state_bytes(void);
+int sb200_gptq4_linear_f16_ex(const void* x_f16, const int32_t* qweight, void* out_f16, const float* bias,
+                              const float* scales, const float* zeros, int64_t m, int64_t k, int64_t n,
+                              int64_t qweight_rows, int group_size, void* state, int flags, void* workspace,
+                              size_t workspace_bytes, void* stream);
 int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_f16, const float* bias,
                            const float* scales, const float* zeros, int64_t m, int64_t k, int64_t n,
                            int64_t qweight_rows, int group_size, void* workspace, size_t workspace_bytes,

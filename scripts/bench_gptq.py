@@ -142,11 +142,36 @@ def run(ms, with_reference=True, quiet=False):
     return totals
 
 
+def run_f16_linear(m=1, quiet=True):
+    """The model path (QuantLinear.forward, fp16 activations): all LLaMA-7B linears through sb200_gptq4_linear_f16_ex, one
+    launch per linear vs the staged path (cast, bias, kernel, cast).  Returns seconds per forward for both."""
+    out = {}
+    for single in (True, False):
+        total = 0.0
+        for name, k, n, cnt in SHAPES:
+            wbytes = k * n // 2
+            copies = max(2, min(24, (256 << 20) // wbytes + 1))
+            ws = make(k, n, copies)
+            x = torch.randn(m, k, device=dev).half()
+            bias = torch.zeros(n, device=dev)
+            t = timeit(lambda i: ops.gptq4_linear_f16(x, ws[i % copies][0], ws[i % copies][1], ws[i % copies][2], bias, 128,
+                                                      static_weights=STATIC, single_launch=single), 200, copies)
+            if not quiet:
+                print(json.dumps({"shape": name, "M": m, "impl": "f16_linear_one_launch" if single else "f16_linear_staged", "us": t * 1e6}))
+            total += t * cnt * LAYERS
+            del ws
+        out["one_launch" if single else "staged"] = total
+    return out
+
+
 def main():
     ms = [int(a) for a in sys.argv[1:]] or [1, 16, 2048]
     totals = run(ms, with_reference=os.environ.get("SB200_NO_REF", "0") != "1")
     for (m, label), t in sorted(totals.items()):
         print(json.dumps({"summary": "llama7b_all_linears", "M": m, "impl": label, "ms_per_forward": t * 1e3, "tok_per_s": m / t}))
+    if 1 in ms:
+        for label, t in run_f16_linear(1, quiet=False).items():
+            print(json.dumps({"summary": "llama7b_all_linears", "M": 1, "impl": "f16_linear_" + label, "ms_per_forward": t * 1e3, "tok_per_s": 1 / t}))
 
 
 if __name__ == "__main__":

@@ -81,6 +81,8 @@ PROTOTYPES = {
     "sb200_gptq4_matmul_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_sz, c_vp]),
     "sb200_gptq4_linear_f16_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "sb200_gptq4_linear_f16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_sz, c_vp]),
+    "sb200_gptq4_linear_f16_state_bytes": (c_sz, []),
+    "sb200_gptq4_linear_f16_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq_matmul": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_sz, c_vp]),
     "sb200_gptq4_set_impl": (c_int, [c_int]),
     "sb200_gptq4_set_trace": (c_int, [c_vp]),

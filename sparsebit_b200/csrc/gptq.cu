@@ -10,7 +10,6 @@
 namespace sb200 {
 int gptq4_simt(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros,
                long long M, long long K, long long N, long long KW, int group_size, cudaStream_t st);
-bool gptq4_decode_supported(const int32_t* qweight, long long N);
 int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
                  long long K, long long N, long long KW, int group_size, int flags, cudaStream_t st);
 bool gptq4_tc_supported(const float* x, const int32_t* qweight, const float* out, long long M, long long K, long long N,
@@ -23,6 +22,11 @@ size_t gptq4_ts_workspace(long long M, long long K, long long N, int group_size)
 int gptq4_ts(const float* x, const int32_t* qweight, float* out, const float* scales, const float* zeros, long long M,
              long long K, long long N, long long KW, int group_size, int chunk_kb, void* workspace, size_t workspace_bytes,
              cudaStream_t st, const __half* x_h = nullptr, __half* out_h = nullptr, const float* bias = nullptr);
+size_t gptq4_decode_f16_partial_bytes(long long M, long long K, long long N);
+int gptq4_decode_f16(const __half* x_h, const int32_t* qweight, __half* out_h, const float* bias, const float* scales,
+                     const float* zeros, long long M, long long K, long long N, long long KW, int group_size, float* partial,
+                     int* counters, int flags, cudaStream_t st);
+bool gptq4_decode_supported(const int32_t* qweight, long long N);
 void gptq4_tc_set_trace(long long* p);
 void gptq4_tc_set_backoff(int ns);
 void gptq4_tc_set_drain(int narrow);
@@ -157,16 +161,32 @@ int sb200_gptq4_matmul_ex(const float* x, const int32_t* qweight, float* out, co
                         workspace_bytes, stream, flags);
 }
 
+constexpr int64_t kF16SingleLaunchMaxM = 32;
+constexpr size_t kF16StateBytes = 65536;  // one int per 128-feature block: N <= 2 097 152
+
 size_t sb200_gptq4_linear_f16_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size) {
   if (m <= 0 || k <= 0 || n <= 0) return 0;
-  // fp32 staging of x and y for the small-M paths + the kernels' own workspace
-  return sb200_gptq4_workspace_bytes(m, k, n, group_size) + (size_t)m * (size_t)(k + n) * sizeof(float) + 2048;
+  // fp32 staging of x and y for the small-M paths + the kernels' own workspace + the per-slice partial sums of the
+  // single-launch decode path
+  const size_t part = m <= kF16SingleLaunchMaxM ? gptq4_decode_f16_partial_bytes(m, k, n) + 256 : 0;
+  return sb200_gptq4_workspace_bytes(m, k, n, group_size) + (size_t)m * (size_t)(k + n) * sizeof(float) + 2048 + part;
 }
+
+size_t sb200_gptq4_linear_f16_state_bytes(void) { return kF16StateBytes; }
 
 int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_f16, const float* bias, const float* scales,
                            const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size,
                            void* workspace, size_t workspace_bytes, void* stream) {
+  return sb200_gptq4_linear_f16_ex(x_f16, qweight, out_f16, bias, scales, zeros, m, k, n, qweight_rows, group_size, nullptr, 0,
+                                   workspace, workspace_bytes, stream);
+}
+
+int sb200_gptq4_linear_f16_ex(const void* x_f16, const int32_t* qweight, void* out_f16, const float* bias, const float* scales,
+                              const float* zeros, int64_t m, int64_t k, int64_t n, int64_t qweight_rows, int group_size,
+                              void* state, int flags, void* workspace, size_t workspace_bytes, void* stream) {
   SB_REQUIRE(x_f16 && qweight && out_f16 && scales && zeros, "sb200_gptq4_linear_f16: null pointer argument");
+  SB_REQUIRE((flags & ~SB200_GPTQ4_STATIC_WEIGHTS) == 0, "sb200_gptq4_linear_f16_ex: unknown flags 0x%x", flags);
+  const int group_size_arg = group_size;  // 0 = one group: handed on unchanged (K itself need not be a multiple of 128)
   SB_REQUIRE(m > 0 && k > 0 && n > 0, "sb200_gptq4_linear_f16: empty operand (M=%lld K=%lld N=%lld)", (long long)m, (long long)k, (long long)n);
   SB_REQUIRE(m < (1LL << 31) && k < (1LL << 31) && n < (1LL << 31), "sb200_gptq4_linear_f16: dimension too large");
   SB_REQUIRE(qweight_rows >= (k + 7) / 8, "sb200_gptq4_linear_f16: qweight has %lld rows, need ceil(K/8) = %lld", (long long)qweight_rows, (long long)((k + 7) / 8));
@@ -183,6 +203,13 @@ int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_
                      gptq4_ts_workspace(m, k, n, group_size) > 0;
   if (ts_ok)  // fp16 in, fp16 out, no fp32 round trip of x or y
     return gptq4_ts(nullptr, qweight, nullptr, scales, zeros, m, k, n, qweight_rows, group_size, 0, workspace, workspace_bytes, st, xh, yh, bias);
+  if (state && m <= kF16SingleLaunchMaxM && gptq4_decode_supported(qweight, n) && n <= (int64_t)(kF16StateBytes / sizeof(int)) * 128) {
+    // decode-sized M with a caller-provided (zero-initialised, self-resetting) arrival-counter state: ONE launch -- fp16
+    // activations are read by the kernel's staging, the last K-slice CTA of every feature block writes bias + sum as fp16
+    float* partial = reinterpret_cast<float*>(((reinterpret_cast<uintptr_t>(workspace) + 255) / 256) * 256);
+    return gptq4_decode_f16(xh, qweight, yh, bias, scales, zeros, m, k, n, qweight_rows, group_size, partial,
+                            reinterpret_cast<int*>(state), flags, st);
+  }
   // small M: stage through fp32 inside the library (a few MB at most) and run the fp32 kernels
   unsigned char* ws = reinterpret_cast<unsigned char*>(((reinterpret_cast<uintptr_t>(workspace) + 255) / 256) * 256);
   float* x32 = reinterpret_cast<float*>(ws);
@@ -194,7 +221,7 @@ int sb200_gptq4_linear_f16(const void* x_f16, const int32_t* qweight, void* out_
   bias_rows_kernel<<<ew_grid(m * n), 256, 0, st>>>(bias, y32, m, n);
   SB_LAUNCHED();
   // the kernel immediately in front is bias_rows_kernel (writes y32 only): the weight tables cannot be its output
-  const int rc = gptq4_dispatch(x32, qweight, y32, scales, zeros, m, k, n, qweight_rows, group_size, 0, 0, rest, rest_bytes, stream,
+  const int rc = gptq4_dispatch(x32, qweight, y32, scales, zeros, m, k, n, qweight_rows, group_size_arg, 0, 0, rest, rest_bytes, stream,
                                 SB200_GPTQ4_STATIC_WEIGHTS);
   if (rc) return rc;
   f32_to_f16_kernel<<<ew_grid(m * n), 256, 0, st>>>(y32, yh, m * n);

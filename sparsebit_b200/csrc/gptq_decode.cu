@@ -67,6 +67,16 @@ struct DecProblem {
   const float* zeros;
   int K, N, KW, G, group_size;
   int colblock_begin;  // first blockIdx.x of this problem
+  // fp16 linear in ONE launch (sb200_gptq4_linear_f16_ex): fp16 activations in, bias + result out as fp16.  The K
+  // slices cannot accumulate into an fp16 tensor, so every slice CTA stores its fp32 partial sums into its own slot of
+  // `partial` ([slices][M][N], plain stores), and the LAST slice CTA of a feature block to arrive (ticket from
+  // `counters[feature block]`, threadfence-reduction pattern) adds the slots in slice order, adds the bias, writes fp16
+  // and resets the counter for the next call: deterministic, no fp32 staging tensors, no cast / bias / cast launches.
+  const __half* x_h;   // nullable: fp16 activations (x is ignored)
+  __half* out_h;       // nullable: fp16 output (out is ignored)
+  const float* bias;   // nullable, fp16 path only
+  float* partial;
+  int* counters;
 };
 constexpr int kDecMaxProblems = 4;
 struct DecBatch {
@@ -103,6 +113,8 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
   float* __restrict__ out = batch.p[pi].out;
   const float* __restrict__ scales = batch.p[pi].scales;
   const float* __restrict__ zeros = batch.p[pi].zeros;
+  const __half* __restrict__ x_h = batch.p[pi].x_h;
+  __half* __restrict__ out_h = batch.p[pi].out_h;
   const int K = batch.p[pi].K, N = batch.p[pi].N, KW = batch.p[pi].KW, G = batch.p[pi].G, group_size = batch.p[pi].group_size;
   const int bx = (int)blockIdx.x - batch.p[pi].colblock_begin;
   const int nblk = (K + kDecBlockK - 1) / kDecBlockK;
@@ -214,12 +226,12 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     float cache[4];  // the values of this warp's first (token, block) pair: read from global memory once
     for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it) {
       const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
-      const float* xr = x + (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
+      const size_t xoff = (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       float amax = 0.f;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int kk = r * 32 + lane;
-        const float v = (blk < nb && (b0 + blk) * kDecBlockK + kk < K) ? __ldg(xr + kk) : 0.f;
+        const float v = (blk < nb && (b0 + blk) * kDecBlockK + kk < K) ? (x_h ? __half2float(__ldg(x_h + xoff + kk)) : __ldg(x + xoff + kk)) : 0.f;
         if (it == 0) cache[r] = v;
         amax = fmaxf(amax, fabsf(v));
       }
@@ -229,7 +241,7 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     __syncthreads();
     for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it) {
       const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
-      const float* xr = x + (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
+      const size_t xoff = (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       const uint32_t abits = s_amax[t];
       // 2^-e with e = floor(log2(amax)) - 14, straight from the exponent field: scaled slice max in [2^14, 2^15)
       const int ex = abits ? (int)(abits >> 23) - 127 - 14 : 0;
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       for (int r = 0; r < 4; ++r) {
         const int kk = r * 32 + lane;
         const bool ok = blk < nb && ((b0 + blk) * kDecBlockK + kk < K);
-        const float v = (it == 0 ? cache[r] : (ok ? __ldg(xr + kk) : 0.f)) * down;
+        const float v = (it == 0 ? cache[r] : (ok ? (x_h ? __half2float(__ldg(x_h + xoff + kk)) : __ldg(x + xoff + kk)) : 0.f)) * down;
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));
         any_lo |= (__half_as_ushort(lo) & 0x7FFFu) != 0;
@@ -350,8 +362,35 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
           for (int j = 0; j < 4; ++j) {
             const int tok = q * 8 + 2 * c + (j & 1), m = m0 + tok;
             const int n = nbase + 2 * T + (j >> 1);
-            if (m < M) atomicAdd(out + (size_t)m * N + n, acc[T][q][j] * escale[tok]);
+            if (m < M) {
+              const float v = acc[T][q][j] * escale[tok];
+              if (out_h) batch.p[pi].partial[((size_t)blockIdx.y * M + m) * N + n] = v;  // this slice's own slot
+              else atomicAdd(out + (size_t)m * N + n, v);
+            }
           }
+    }
+  }
+  if (out_h) {
+    // last slice CTA of this feature block adds the slots in slice order (threadfence-reduction pattern)
+    __shared__ int s_last;
+    const int slices_p = (nblk + blocks_per_slice - 1) / blocks_per_slice;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(batch.p[pi].counters + bx, 1) == slices_p - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int n = bx * kDecCols + tid;
+      if (n < N) {
+        const float* __restrict__ part = batch.p[pi].partial;
+        const float bv = batch.p[pi].bias ? __ldg(batch.p[pi].bias + n) : 0.f;
+        for (int m = 0; m < M; ++m) {
+          float t = 0.f;
+          for (int sl = 0; sl < slices_p; ++sl) t += __ldcg(part + ((size_t)sl * M + m) * N + n);
+          out_h[(size_t)m * N + n] = __float2half_rn(t + bv);
+        }
+      }
+      if (tid == 0) batch.p[pi].counters[bx] = 0;  // ready for the next call on this state
     }
   }
 }
@@ -439,6 +478,38 @@ int gptq4_decode(const float* x, const int32_t* qweight, float* out, const float
   p.G = (int)((K + group_size - 1) / group_size);
   p.group_size = group_size;
   p.colblock_begin = 0;
+  p.x_h = nullptr;
+  p.out_h = nullptr;
+  p.bias = nullptr;
+  p.partial = nullptr;
+  p.counters = nullptr;
+  return gptq4_decode_batch(&p, 1, M, flags, st);
+}
+
+// fp16 in / fp16 out in one launch; `partial` holds ceil(K / 128) * M * N floats, `counters` ceil(N / 128) zeroed ints
+size_t gptq4_decode_f16_partial_bytes(long long M, long long K, long long N) {
+  return (size_t)((K + kDecBlockK - 1) / kDecBlockK) * (size_t)M * (size_t)N * sizeof(float);
+}
+int gptq4_decode_f16(const __half* x_h, const int32_t* qweight, __half* out_h, const float* bias, const float* scales,
+                     const float* zeros, long long M, long long K, long long N, long long KW, int group_size, float* partial,
+                     int* counters, int flags, cudaStream_t st) {
+  DecProblem p;
+  p.x = nullptr;
+  p.qw = reinterpret_cast<const uint32_t*>(qweight);
+  p.out = nullptr;
+  p.scales = scales;
+  p.zeros = zeros;
+  p.K = (int)K;
+  p.N = (int)N;
+  p.KW = (int)KW;
+  p.G = (int)((K + group_size - 1) / group_size);
+  p.group_size = group_size;
+  p.colblock_begin = 0;
+  p.x_h = x_h;
+  p.out_h = out_h;
+  p.bias = bias;
+  p.partial = partial;
+  p.counters = counters;
   return gptq4_decode_batch(&p, 1, M, flags, st);
 }
 
@@ -475,6 +546,11 @@ extern "C" int sb200_gptq4_matmul_batch_ex(const sb200_gptq4_problem* problems, 
     p[i].G = (int)((q.k + gs - 1) / gs);
     p[i].group_size = gs;
     p[i].colblock_begin = 0;
+    p[i].x_h = nullptr;
+    p[i].out_h = nullptr;
+    p[i].bias = nullptr;
+    p[i].partial = nullptr;
+    p[i].counters = nullptr;
   }
   return gptq4_decode_batch(p, count, m, flags, (cudaStream_t)stream);
 }

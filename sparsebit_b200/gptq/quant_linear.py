@@ -156,11 +156,15 @@ class QuantLinear(nn.Module):
             # fp32 copy of the result (the reference casts all of them every forward, utils/quant.py:262-278)
             from .. import ops
 
-            if getattr(self, "_f32_tables", None) is None or self._f32_tables[0].device != x.device:
+            fresh = getattr(self, "_f32_tables", None) is None or self._f32_tables[0].device != x.device
+            if fresh:
                 self._f32_tables = (self.scales.float().contiguous().to(x.device), self.zeros.float().contiguous().to(x.device),
                                     self.bias.float().contiguous().to(x.device))
             sc, zr, bs = self._f32_tables
-            return ops.gptq4_linear_f16(x.contiguous(), self.qweight, sc, zr, bs, 0 if self.groupsize == -1 else self.groupsize)
+            # the buffers of a loaded model are constants (SB200_GPTQ4_STATIC_WEIGHTS) -- except in the call that has
+            # just produced the fp32 tables with the kernels immediately in front of this one
+            return ops.gptq4_linear_f16(x.contiguous(), self.qweight, sc, zr, bs, 0 if self.groupsize == -1 else self.groupsize,
+                                        static_weights=not fresh)
         # fp32 math like the reference (utils/quant.py:262-278), result cast back to x.dtype
         y = QuantMatmul.apply(x.float(), self.qweight, self.scales.float(), self.zeros.float(), self.bias.float(),
                               self.groupsize, self.bit)

@@ -591,8 +591,13 @@ def gptq4_matmul_batch(problems, group_size=0, static_weights=False):
     return [p[2] for p in problems]
 
 
-def gptq4_linear_f16(x, qweight, scales, zeros, bias=None, group_size=0):
-    """fp16 activations in, fp16 ``bias + x @ dequant(qweight)`` out, no eager casts (sb200_gptq4_linear_f16)."""
+_gptq_state = {}  # (device, stream) -> zero-initialised, self-resetting arrival counters of the single-launch decode path
+
+
+def gptq4_linear_f16(x, qweight, scales, zeros, bias=None, group_size=0, static_weights=False, single_launch=True):
+    """fp16 activations in, fp16 ``bias + x @ dequant(qweight)`` out, no eager casts (sb200_gptq4_linear_f16_ex).
+    Decode-sized M (<= 32) is ONE kernel launch; ``single_launch=False`` keeps the staged path (cast, bias, kernel, cast).
+    ``static_weights``: see ``gptq4_matmul``."""
     lib = _lib.load()
     _req(x, "inp1", torch.float16), _req(scales, "scales"), _req(zeros, "zeros"), _req(qweight, "inp2", torch.int32)
     if bias is not None:
@@ -607,10 +612,18 @@ def gptq4_linear_f16(x, qweight, scales, zeros, bias=None, group_size=0):
     if ws is None or ws.numel() < ws_bytes:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         _gptq_ws[key] = ws
+    state = None
+    if single_launch and m <= 32:
+        skey = key[:2]
+        state = _gptq_state.get(skey)
+        if state is None:
+            state = torch.zeros(int(lib.sb200_gptq4_linear_f16_state_bytes()), dtype=torch.uint8, device=x.device)
+            _gptq_state[skey] = state
     with torch.cuda.device(x.device):
-        check(lib.sb200_gptq4_linear_f16(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                         scales.data_ptr(), zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size), ws.data_ptr(),
-                                         ws_bytes, _stream(x)))
+        check(lib.sb200_gptq4_linear_f16_ex(x.data_ptr(), qweight.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                            scales.data_ptr(), zeros.data_ptr(), m, k, n, qweight.shape[0], int(group_size),
+                                            state.data_ptr() if state is not None else None,
+                                            GPTQ4_STATIC_WEIGHTS if static_weights else 0, ws.data_ptr(), ws_bytes, _stream(x)))
     return out
 
 

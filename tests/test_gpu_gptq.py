@@ -269,6 +269,76 @@ def test_linear_f16_entry_point(m, k, n, gs):
     np.testing.assert_allclose(y_nobias, exp - bias, rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("m,k,n,gs", [(1, 4096, 4096, 128), (1, 1000, 132, -1), (9, 1024, 520, 128), (17, 2048, 1028, 256), (32, 1536, 384, 384)])
+def test_linear_f16_decode_sized_is_one_launch(m, k, n, gs):
+    """sb200_gptq4_linear_f16_ex with a counter state: fp16 in -> ONE decode-kernel launch -> fp16 bias + x @ W out (the
+    last K-slice CTA of every feature block adds the slices' partial sums in slice order).  Repeated calls on the same
+    state (the counters reset themselves), equal to the staged four-launch path up to fp32 summation order, and
+    bit-identical run to run."""
+    from sparsebit_b200 import launch_count, ops
+
+    rng = np.random.default_rng(3 * m + k + n)
+    x, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, gs)
+    xh = x.astype(np.float16)
+    g = 0 if gs == -1 else gs
+    args = (t(xh), t(qw), t(scales), t(zeros), t(bias), g)
+    before = launch_count()
+    y_a = ops.gptq4_linear_f16(*args)
+    assert launch_count() - before == 1
+    y_b = ops.gptq4_linear_f16(*args, static_weights=True)  # second call on the same state; weights requested before the wait
+    y_c = ops.gptq4_linear_f16(*args)
+    before = launch_count()
+    y_staged = ops.gptq4_linear_f16(*args, single_launch=False)
+    assert launch_count() - before == 4
+    a = y_a.cpu().numpy()
+    assert a.dtype == np.float16 and a.shape == (m, n)
+    assert np.array_equal(a, y_b.cpu().numpy()) and np.array_equal(a, y_c.cpu().numpy())  # fixed summation order
+    exp = ogptq.dequant_matmul(xh.astype(np.float32), qw, np.broadcast_to(bias, (m, n)), scales, zeros, g)
+    ulp = np.abs(exp).astype(np.float16).astype(np.float32) * 2.0**-10 + 2.0**-24
+    assert np.all(np.abs(a.astype(np.float64) - exp) <= 0.51 * ulp + 1e-5 * (1 + np.abs(exp)))
+    assert np.all(np.abs(y_staged.cpu().numpy().astype(np.float64) - exp) <= 0.51 * ulp + 1e-5 * (1 + np.abs(exp)))
+    y_nobias = ops.gptq4_linear_f16(t(xh), t(qw), t(scales), t(zeros), None, g).cpu().numpy().astype(np.float32)
+    np.testing.assert_allclose(y_nobias, exp - bias, rtol=2e-3, atol=2e-3)
+
+
+def test_linear_f16_single_launch_inside_a_cuda_graph():
+    """Three dependent fp16 linears (each consumes its predecessor's fp16 output) captured into one CUDA graph and
+    replayed: the self-resetting counters and the programmatic launches must survive replays."""
+    from sparsebit_b200 import ops
+
+    rng = np.random.default_rng(11)
+    dims = [(1024, 768), (768, 1536), (1536, 256)]
+    m = 2
+    layers = []
+    for k, n in dims:
+        _, qw, bias, scales, zeros = _make_case(rng, (m,), k, n, 128)
+        layers.append((t(qw), t(scales), t(zeros), t(bias), qw, scales, zeros, bias))
+    x = rng.standard_normal((m, dims[0][0])).astype(np.float16)
+    xt = t(x)
+
+    def chain():
+        cur = xt
+        for qw, sc, zr, bs, *_ in layers:
+            cur = ops.gptq4_linear_f16(cur, qw, sc, zr, bs, 128, static_weights=True)
+        return cur
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        chain()
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            out = chain()
+    for _ in range(3):
+        gr.replay()
+    torch.cuda.synchronize()
+    exp = x.astype(np.float32)
+    for *_, qw, scales, zeros, bias in layers:
+        exp = ogptq.dequant_matmul(exp, qw, np.broadcast_to(bias, (m, qw.shape[1])), scales, zeros, 128).astype(np.float16).astype(np.float32)
+    np.testing.assert_allclose(out.cpu().numpy().astype(np.float32), exp, rtol=4e-3, atol=4e-3 * np.abs(exp).max())
+
+
 def test_tcgen05_forced_on_unsupported_shape_is_an_error():
     lib = _lib.load()
     rng = np.random.default_rng(1)
