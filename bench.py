@@ -272,23 +272,27 @@ def block_calibration(dev, world, rank, peak, blocks=12, shard=128):
     elems = sum(x.numel() for x in data)
     passes = {"minmax": 1, "mse": 2, "percentile": 3}  # reads of the shard: running min/max (+ sweep | 3 radix passes)
     res = {"workload": f"DeiT-base activation sites x{blocks} blocks, {shard} samples per GPU (BASELINE configs[2]), {len(data)} quantizers, "
-                       f"{elems} elems per GPU", "world": world, "observers": {}}
+                       f"{elems} elems per GPU", "world": world, "timing": "second of two sweeps (the first warms NCCL connections and the allocator)",
+           "observers": {}}
     check = {}
     for observer in ("minmax", "mse", "percentile"):
-        qs = make_quantizers(len(data), observer)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sbdist.collectives(reset=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record()
-        for q, x in zip(qs, data):
-            q.update_observer(x, alias_ok=True)
-        sbdist.drive_all([q.calc_qparams_steps() for q in qs])
-        e1.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
+        # one untimed warm-up sweep (the first NCCL collective of a given size pays ~30 ms of connection set-up; caching
+        # allocator growth), then the timed one on fresh quantizers
+        for timed in (False, True):
+            qs = make_quantizers(len(data), observer)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sbdist.collectives(reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for q, x in zip(qs, data):
+                q.update_observer(x, alias_ok=True)
+            sbdist.drive_all([q.calc_qparams_steps() for q in qs])
+            e1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
         tt = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -386,7 +386,13 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
         const float bv = batch.p[pi].bias ? __ldg(batch.p[pi].bias + n) : 0.f;
         for (int m = 0; m < M; ++m) {
           float t = 0.f;
-          for (int sl = 0; sl < slices_p; ++sl) t += __ldcg(part + ((size_t)sl * M + m) * N + n);
+          int sl = 0;
+          for (; sl + 3 < slices_p; sl += 4) {  // four loads in flight, summed in slice order
+            const float v0 = __ldcg(part + ((size_t)sl * M + m) * N + n), v1 = __ldcg(part + ((size_t)(sl + 1) * M + m) * N + n),
+                        v2 = __ldcg(part + ((size_t)(sl + 2) * M + m) * N + n), v3 = __ldcg(part + ((size_t)(sl + 3) * M + m) * N + n);
+            t = (((t + v0) + v1) + v2) + v3;
+          }
+          for (; sl < slices_p; ++sl) t += __ldcg(part + ((size_t)sl * M + m) * N + n);
           out_h[(size_t)m * N + n] = __float2half_rn(t + bv);
         }
       }

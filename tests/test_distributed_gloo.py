@@ -45,8 +45,15 @@ def _worker(rank, world, port, out):
     sse = torch.full((2, 3), 0.5 + rank, dtype=torch.float64)
     sbdist.sync_sum([hist])
     sbdist.sync_sum([sse])
+    # one packed call with mixed dtypes, a 2-D tensor and a non-contiguous view (packed per dtype, one collective)
+    m1 = torch.arange(6, dtype=torch.int64).reshape(2, 3) * (rank + 1)
+    m2 = torch.full((4,), 0.25 * (rank + 1), dtype=torch.float64)
+    m3 = (torch.arange(8, dtype=torch.float32).reshape(2, 4) * (rank + 1)).t()
+    before = sbdist.collectives()["sum"]
+    sbdist.sync_sum([m1, m2, m3])
+    assert sbdist.collectives()["sum"] == before + 1
     if rank == 0:
-        torch.save({"s0": _dec(states[0]), "s1": _dec(states[1]), "hist": hist, "sse": sse}, out)
+        torch.save({"s0": _dec(states[0]), "s1": _dec(states[1]), "hist": hist, "sse": sse, "m1": m1, "m2": m2, "m3": m3.contiguous()}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,6 +83,9 @@ def test_stat_allreduce_world2(tmp_path):
         np.testing.assert_array_equal(got[key][:, 1], mx)
     assert torch.equal(got["hist"], torch.arange(8, dtype=torch.int64) * 3)
     assert torch.equal(got["sse"], torch.full((2, 3), 2.0, dtype=torch.float64))
+    assert torch.equal(got["m1"], torch.arange(6, dtype=torch.int64).reshape(2, 3) * 3)
+    assert torch.equal(got["m2"], torch.full((4,), 0.75, dtype=torch.float64))
+    assert torch.equal(got["m3"], (torch.arange(8, dtype=torch.float32).reshape(2, 4) * 3).t().contiguous())
 
 
 def test_pack_unpack_roundtrip_without_process_group():
