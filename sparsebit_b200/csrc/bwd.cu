@@ -222,6 +222,29 @@ __global__ void __launch_bounds__(128) bwd_cols_kernel(const float* __restrict__
     const float4* g4 = reinterpret_cast<const float4*>(gy) + q;
     float4* o4 = reinterpret_cast<float4*>(gx) + q;
     long long r = r0;
+    auto row = [&](const float4& xv, const float4& gv, long long rr) {
+      float4 o;
+      o.x = bwd1<ROUNDING>(xv.x, gv.x, p[0], lo_term[0], hi_term[0], a[0], rounding);
+      o.y = bwd1<ROUNDING>(xv.y, gv.y, p[1 % VEC], lo_term[1 % VEC], hi_term[1 % VEC], a[1 % VEC], rounding);
+      o.z = bwd1<ROUNDING>(xv.z, gv.z, p[2 % VEC], lo_term[2 % VEC], hi_term[2 % VEC], a[2 % VEC], rounding);
+      o.w = bwd1<ROUNDING>(xv.w, gv.w, p[3 % VEC], lo_term[3 % VEC], hi_term[3 % VEC], a[3 % VEC], rounding);
+      st_stream4(o4 + rr * nq, o);
+    };
+    for (; r + 3 < r1; r += 4) {  // eight independent 128-bit loads in flight per thread (12 B/elem of traffic to cover)
+      const float4 xa = ld_stream4(x4 + r * nq), ga = ld_stream4(g4 + r * nq);
+      const float4 xb = ld_stream4(x4 + (r + 1) * nq), gb = ld_stream4(g4 + (r + 1) * nq);
+      const float4 xc = ld_stream4(x4 + (r + 2) * nq), gc = ld_stream4(g4 + (r + 2) * nq);
+      const float4 xd = ld_stream4(x4 + (r + 3) * nq), gd = ld_stream4(g4 + (r + 3) * nq);
+      row(xa, ga, r);
+      row(xb, gb, r + 1);
+      row(xc, gc, r + 2);
+      row(xd, gd, r + 3);
+      if ((k += 4) >= 256) {  // bound the fp32 accumulation length
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { d0[j] += a[j].gs; d1[j] += a[j].gzp; a[j].gs = a[j].gzp = 0.f; }
+        k = 0;
+      }
+    }
     for (; r + 1 < r1; r += 2) {
       const float4 xa = ld_stream4(x4 + r * nq), ga = ld_stream4(g4 + r * nq);
       const float4 xb = ld_stream4(x4 + (r + 1) * nq), gb = ld_stream4(g4 + (r + 1) * nq);
@@ -301,9 +324,17 @@ static inline int persistent_grid(long long tiles, int ctas_per_sm) {
   return (int)(tiles < cap ? tiles : cap);
 }
 
+// Threads per CTA of the channel-last kernels: 64 when that leaves fewer idle lanes in the last CTA of a row (192 vector
+// columns of a 768-channel tensor: 2 x 128 wastes a quarter of the threads, 3 x 64 none), else 128.
+static inline int cols_block_threads(long long channels) {
+  const long long nq = (channels % 4 == 0) ? channels / 4 : channels;
+  const long long w128 = (nq + 127) / 128 * 128 - nq, w64 = (nq + 63) / 64 * 64 - nq;
+  return w64 < w128 ? 64 : 128;
+}
 static inline long long cols_row_blocks(long long outer, long long channels) {
-  const long long gx = (((channels % 4 == 0) ? channels / 4 : channels) + 127) / 128;
-  long long want = ((long long)sm_count() * 8 + gx - 1) / gx;
+  const int bt = cols_block_threads(channels);
+  const long long gx = (((channels % 4 == 0) ? channels / 4 : channels) + bt - 1) / bt;
+  long long want = ((long long)sm_count() * 8 * (128 / bt) + gx - 1) / gx;
   if (want > outer) want = outer;
   if (want > 65535) want = 65535;
   if (want < 1) want = 1;
@@ -342,9 +373,10 @@ static int bwd_dispatch(const float* x, const float* scale, const float* zp, con
     // cols_row_blocks sizes the grid for the vector layout when C % 4 == 0; the scalar fallback only
     // gets more thread blocks along x, the partial layout [row block][C] is the same.
     const long long nqv = vec ? channels / 4 : channels;
-    const dim3 grid((unsigned)((nqv + 127) / 128), (unsigned)nb);
+    const int bt = cols_block_threads(channels);
+    const dim3 grid((unsigned)((nqv + bt - 1) / bt), (unsigned)nb);
 #define SB_GOC(V_, R_) \
-  bwd_cols_kernel<V_, R_><<<grid, 128, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, gz_hi, rounding, partial)
+  bwd_cols_kernel<V_, R_><<<grid, bt, 0, st>>>(x, gy, gx, scale, zp, outer, (int)channels, rpb, (float)qmin, (float)qmax, gz_hi, rounding, partial)
     if (vec) {
       if (rounding == 0) SB_GOC(4, 0); else SB_GOC(4, -1);
     } else {
