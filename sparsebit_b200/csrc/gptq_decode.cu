@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     // per-token power-of-two scale, fp16 hi / lo planes, 8-K permutation, per-block row sums
     const int pairs = tokens * blocks_per_slice;
     float cache[4];  // the values of this warp's first (token, block) pair: read from global memory once
-    for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it) {
+    // fp16 activations (x_h) are their own hi plane: no per-token power-of-two scale, no lo plane -- the abs-max pass is skipped
+    for (int p = warp, it = 0; p < pairs && !x_h; p += kDecThreads / 32, ++it) {
       const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
       const size_t xoff = (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       float amax = 0.f;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       const size_t xoff = (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       const uint32_t abits = s_amax[t];
       // 2^-e with e = floor(log2(amax)) - 14, straight from the exponent field: scaled slice max in [2^14, 2^15)
-      const int ex = abits ? (int)(abits >> 23) - 127 - 14 : 0;
+      const int ex = (abits && !x_h) ? (int)(abits >> 23) - 127 - 14 : 0;
       const float down = __uint_as_float((uint32_t)(127 - max(-126, min(127, ex))) << 23);
       if (lane == 0 && blk == 0) escale[t] = __uint_as_float((uint32_t)(127 + max(-126, min(127, ex))) << 23);
       float s = 0.f;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       for (int r = 0; r < 4; ++r) {
         const int kk = r * 32 + lane;
         const bool ok = blk < nb && ((b0 + blk) * kDecBlockK + kk < K);
-        const float v = (it == 0 ? cache[r] : (ok ? (x_h ? __half2float(__ldg(x_h + xoff + kk)) : __ldg(x + xoff + kk)) : 0.f)) * down;
+        const float v = ((it == 0 && !x_h) ? cache[r] : (ok ? (x_h ? __half2float(__ldg(x_h + xoff + kk)) : __ldg(x + xoff + kk)) : 0.f)) * down;
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));
         any_lo |= (__half_as_ushort(lo) & 0x7FFFu) != 0;

@@ -134,11 +134,25 @@ stream_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, flo
             for (int j = 0; j < VEC; ++j) a[u][j] = qdq1<ROUNDING>(a[u][j], p, rounding);
           } else {  // MODE_CHANNEL
             if (use_tab) {
-              if (pos + (VEC - 1) < g.inner) {  // whole vector inside one channel row
+              // Warp-uniform choice: with short rows (7 x 7 maps: inner = 49) one lane in sixteen holds a vector that
+              // straddles a channel boundary, i.e. nearly every warp does -- a per-lane branch would run the whole
+              // warp through both paths.  When any lane straddles, all lanes take the two-entry select path below.
+              const bool cross = pos + (VEC - 1) >= g.inner;
+              const bool any_cross = __any_sync(__activemask(), cross);
+              if (!any_cross) {  // whole vector inside one channel row
                 const float4 t = s_tab[c];
                 p.s = t.x; p.r = t.y; p.zp = t.z; p.fast = t.w != 0.f;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) a[u][j] = qdq1<ROUNDING, true>(a[u][j], p, rounding);
+              } else if (g.inner >= VEC) {  // at most ONE boundary inside the vector: this channel's entry or the next one's
+                const float4 t0 = s_tab[c];
+                const float4 t1 = s_tab[(c + 1 == g.channels) ? 0 : c + 1];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                  const bool nx = pos + j >= g.inner;
+                  p.s = nx ? t1.x : t0.x; p.r = nx ? t1.y : t0.y; p.zp = nx ? t1.z : t0.z; p.fast = (nx ? t1.w : t0.w) != 0.f;
+                  a[u][j] = qdq1<ROUNDING, true>(a[u][j], p, rounding);
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
