@@ -96,6 +96,32 @@ def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0
 
 
 # --------------------------------------------------------------------------------------------
+# DoReFa (sparsebit/quantization/quantizers/dorefa.py:15-26): tanh squash + abs-max normalise in front of the STE.
+def dorefa_normalise(x):
+    """dorefa.py:16-17 / :24-25: ``t = x.tanh(); t / t.abs().max()`` in fp32 (numpy's tanh may differ from ATen's by an
+    ulp: compare downstream results with a small allowance for rounding flips)."""
+    with np.errstate(all="ignore"):
+        t = np.tanh(np.asarray(x, dtype=F32)).astype(F32)
+        m = np.abs(t).max().astype(F32)
+        return (t / m).astype(F32), t, m
+
+
+def dorefa_forward(x, scale, zero_point, qmin, qmax, ch_axis=0):
+    """dorefa.py:15-20: fake-quant of the normalised tensor."""
+    xn, _, _ = dorefa_normalise(x)
+    return qdq(xn, scale, zero_point, qmin, qmax, ch_axis)
+
+
+def dorefa_grad_x(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0):
+    """Autograd of the same chain with scale / zero_point as buffers: STE mask (quant_tensor.py:59-64) -> ``/ max`` ->
+    tanh' = 1 - t^2, op by op in fp32 like ATen's div / tanh backward."""
+    xn, t, m = dorefa_normalise(x)
+    gx_ste, _, _ = ste_backward(xn, scale, zero_point, grad_y, qmin, qmax, ch_axis)
+    with np.errstate(all="ignore"):
+        return ((gx_ste / m).astype(F32) * (F32(1) - (t * t).astype(F32)).astype(F32)).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------
 # AdaRound (sparsebit/quantization/quantizers/adaround.py) -- the quantizer that bypasses STE.
 _STRETCH = F32(1.1 - (-0.1))  # zeta - gamma in Python doubles, narrowed to the tensor dtype by ATen
 _GAMMA = F32(-0.1)

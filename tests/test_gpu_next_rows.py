@@ -287,6 +287,13 @@ def test_dorefa_fused_kernels_match_the_eager_chain(scheme, shape):
     z = q.zero_point.detach().reshape([-1] + [1] * (len(shape) - 1)).cpu().numpy() if q.scale.numel() > 1 else float(q.zero_point)
     k = a / s + np.rint(z)
     assert np.abs(k - np.rint(k)).max() < 1e-3 and k.min() >= qmin - 1e-3 and k.max() <= qmax + 1e-3
+    # the numpy restatement of the reference chain (oracle.qdq.dorefa_*, pinned to the reference's own DoReFa output):
+    # numpy's tanh may differ from libdevice's by an ulp, so a few values may sit on the neighbouring grid point
+    sc_np, zp_np = q.scale.detach().reshape(-1).cpu().numpy(), q.zero_point.detach().reshape(-1).cpu().numpy()
+    exp = oqdq.dorefa_forward(x.cpu().numpy(), sc_np, zp_np, qmin, qmax, ch_axis=0)
+    assert np.mean(a != exp) < 5e-3, (scheme, np.mean(a != exp))
+    egx = oqdq.dorefa_grad_x(x.cpu().numpy(), sc_np, zp_np, gy.cpu().numpy(), qmin, qmax, ch_axis=0)
+    assert np.mean(~np.isclose(ga, egx, rtol=1e-4, atol=1e-6)) < 5e-3, scheme
 
 
 def test_dorefa_nan_and_ragged_inputs():

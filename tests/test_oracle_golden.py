@@ -208,6 +208,24 @@ def test_adaround_restatement_matches_reference(golden):
                                    rtol=1e-5, atol=1e-8, err_msg=name)
 
 
+def test_dorefa_restatement_matches_reference(golden):
+    """oracle.qdq.dorefa_forward against the reference's DoReFa quantizer output (dorefa.py:15-20); numpy's tanh may
+    differ from ATen's by an ulp, which can move a value across a rounding boundary: a few grid flips are allowed."""
+    g = golden("next_rows")
+    x = g["dorefa_w4_x0"]
+    qmin, qmax = (int(v) for v in g["dorefa_w4_meta"][:2])
+    y = oqdq.dorefa_forward(x, g["dorefa_w4_scale"], g["dorefa_w4_zp"], qmin, qmax)
+    assert np.mean(y != g["dorefa_w4_y"]) < 5e-3
+    step = float(g["dorefa_w4_scale"][0])
+    assert np.abs(y - g["dorefa_w4_y"]).max() <= step * 1.0001  # a flip moves a value by exactly one grid step
+    xn, t, m = oqdq.dorefa_normalise(x)
+    assert np.abs(xn).max() == 1.0 and m == np.abs(np.tanh(x.astype(np.float32))).max()
+    # gradient restatement: finite-difference-free sanity -- zero where the STE masks, else gy / m * (1 - t^2)
+    gy = np.ones_like(x)
+    gx = oqdq.dorefa_grad_x(x, g["dorefa_w4_scale"], g["dorefa_w4_zp"], gy, qmin, qmax)
+    assert gx.shape == x.shape and np.all(gx >= 0) and np.all(gx <= 1.0 / m + 1e-6)
+
+
 def test_gptq_lowbit_matches_reference(golden):
     """3-bit / 2-bit packing + matmul restatement vs the reference's QuantLinear.pack and its
     Linear(dequantised W) ground truth (test_cuda_kernel.py bit=2,3 cases, scaled down)."""
