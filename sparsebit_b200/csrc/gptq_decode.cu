@@ -197,8 +197,12 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
   // of the packed weights themselves
   {
     const int n = bx * kDecCols + tid;
+    // quantisation group of each 128-K block, advanced incrementally (one integer division per CTA, not one per block)
+    int grp = (b0 * kDecBlockK) / group_size;
+    long long kend = (long long)(grp + 1) * group_size;  // first k of group grp + 1
     for (int bl = 0; bl < nb; ++bl) {
-      const int grp = ((b0 + bl) * kDecBlockK) / group_size;
+      const long long k0 = (long long)(b0 + bl) * kDecBlockK;
+      while (k0 >= kend) { ++grp; kend += group_size; }
       s_sc[bl * kDecCols + tid] = n < N ? __ldg(scales + (size_t)n * G + grp) : 0.f;
       s_zr[bl * kDecCols + tid] = n < N ? __ldg(zeros + (size_t)n * G + grp) : 0.f;
     }
@@ -225,8 +229,14 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
     const int pairs = tokens * blocks_per_slice;
     float cache[4];  // the values of this warp's first (token, block) pair: read from global memory once
     // fp16 activations (x_h) are their own hi plane: no per-token power-of-two scale, no lo plane -- the abs-max pass is skipped
-    for (int p = warp, it = 0; p < pairs && !x_h; p += kDecThreads / 32, ++it) {
-      const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
+    // (token, block) of this warp's pair, advanced by 4 pairs per iteration without a division per iteration
+    const int t_first = warp / blocks_per_slice, blk_first = warp - t_first * blocks_per_slice;
+    int t = t_first, blk = blk_first;
+    auto next_pair = [&]() {
+      blk += kDecThreads / 32;
+      while (blk >= blocks_per_slice) { blk -= blocks_per_slice; ++t; }
+    };
+    for (int p = warp, it = 0; p < pairs && !x_h; p += kDecThreads / 32, ++it, next_pair()) {
       const size_t xoff = (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       float amax = 0.f;
 #pragma unroll
@@ -240,8 +250,9 @@ __global__ void __launch_bounds__(kDecThreads) gptq4_decode_kernel(const __grid_
       if (lane == 0 && amax < __int_as_float(0x7f800000)) atomicMax(&s_amax[t], __float_as_uint(amax));  // non-negative: bit order == value order
     }
     __syncthreads();
-    for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it) {
-      const int t = p / blocks_per_slice, blk = p - t * blocks_per_slice;
+    t = t_first;
+    blk = blk_first;
+    for (int p = warp, it = 0; p < pairs; p += kDecThreads / 32, ++it, next_pair()) {
       const size_t xoff = (size_t)(m0 + t) * K + (size_t)(b0 + blk) * kDecBlockK;
       const uint32_t abits = s_amax[t];
       // 2^-e with e = floor(log2(amax)) - 14, straight from the exponent field: scaled slice max in [2^14, 2^15)
