@@ -376,8 +376,8 @@ int sb200_gptq4_matmul_batch_ex(const sb200_gptq4_problem* problems, int count, 
  *   out_f16[m, n] = fp16( bias[n] + sum_k (scales * q - zeros) * x_f16[m, k] )          (overwrites out_f16)
  * bias may be NULL; scales / zeros are the fp32 [N, G] tables.  Prefill-sized M runs the tensor-memory-operand
  * tcgen05 kernel directly on the fp16 activations (their hi plane, no lo pass) and writes fp16 from the epilogue;
- * smaller M is staged through fp32 inside the library.  Same accuracy as the fp32 entry point before the final
- * rounding to fp16.  workspace: sb200_gptq4_linear_f16_workspace_bytes(...) bytes. */
+ * smaller M is staged through fp32 inside the library (cast, bias, kernel, cast) -- or runs as ONE launch through
+ * sb200_gptq4_linear_f16_ex below.  Same accuracy as the fp32 entry point before the final rounding to fp16.  workspace: sb200_gptq4_linear_f16_workspace_bytes(...) bytes. */
 size_t sb200_gptq4_linear_f16_workspace_bytes(int64_t m, int64_t k, int64_t n, int group_size);
 /* Decode-sized M (<= 32) in ONE launch: the decode kernel reads the fp16 activations itself, every K-slice CTA stores its
  * fp32 partial sums into its own slot of the workspace and the last slice CTA of a 128-feature block to arrive adds the
