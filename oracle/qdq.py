@@ -96,6 +96,23 @@ def ste_backward(x, scale, zero_point, grad_y, qmin, qmax, ch_axis=0, rounding=0
 
 
 # --------------------------------------------------------------------------------------------
+# PACT (sparsebit/quantization/quantizers/pact.py:43-46): torch.clamp(x, lower, alpha) in front of the STE.
+def clamp_backward(x, grad_y, lo, hi):
+    """Gradients of ``torch.clamp(x, lo, hi)`` with tensor bounds (ATen's convention: the closed interval passes the
+    gradient to x, values above ``hi`` send it to ``hi``, values below ``lo`` to ``lo``); sums in fp64.
+    Returns gx (fp32), g_hi, g_lo (fp64 scalars).  For the symmetric range PACT uses lower = -alpha, so
+    d/d alpha = g_hi - g_lo; for the unsigned range lower is a constant zero and d/d alpha = g_hi."""
+    x = np.asarray(x, dtype=F32)
+    gy = np.asarray(grad_y, dtype=F32)
+    lo, hi = F32(lo), F32(hi)
+    inside = (x >= lo) & (x <= hi)
+    gx = np.where(inside, gy, F32(0)).astype(F32)
+    g_hi = gy.astype(np.float64)[x > hi].sum()
+    g_lo = gy.astype(np.float64)[x < lo].sum()
+    return gx, g_hi, g_lo
+
+
+# --------------------------------------------------------------------------------------------
 # DoReFa (sparsebit/quantization/quantizers/dorefa.py:15-26): tanh squash + abs-max normalise in front of the STE.
 def dorefa_normalise(x):
     """dorefa.py:16-17 / :24-25: ``t = x.tanh(); t / t.abs().max()`` in fp32 (numpy's tanh may differ from ATen's by an

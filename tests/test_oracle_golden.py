@@ -208,6 +208,26 @@ def test_adaround_restatement_matches_reference(golden):
                                    rtol=1e-5, atol=1e-8, err_msg=name)
 
 
+def test_clamp_backward_restatement_matches_aten_autograd():
+    """oracle.qdq.clamp_backward against autograd through torch.clamp with tensor bounds (what pact.py:43-46 runs), incl.
+    values exactly on the bounds."""
+    import torch
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 7, 11, generator=g) * 2
+    x.view(-1)[:4] = torch.tensor([1.5, -1.5, 1.5000001, -1.5000001])
+    gy = torch.randn(x.shape, generator=g)
+    for symmetric in (True, False):
+        alpha = torch.tensor([1.5], requires_grad=True)
+        xr = x.clone().requires_grad_(True)
+        lower = -alpha if symmetric else torch.zeros(1)
+        torch.clamp(xr, lower, alpha).backward(gy)
+        gx, g_hi, g_lo = oqdq.clamp_backward(x.numpy(), gy.numpy(), float(lower), 1.5)
+        assert np.array_equal(gx, xr.grad.numpy())
+        expect = g_hi - g_lo if symmetric else g_hi
+        np.testing.assert_allclose(float(alpha.grad), expect, rtol=1e-5)
+
+
 def test_dorefa_restatement_matches_reference(golden):
     """oracle.qdq.dorefa_forward against the reference's DoReFa quantizer output (dorefa.py:15-20); numpy's tanh may
     differ from ATen's by an ulp, which can move a value across a rounding boundary: a few grid flips are allowed."""
