@@ -222,7 +222,7 @@ def test_clamp_backward_restatement_matches_aten_autograd():
         xr = x.clone().requires_grad_(True)
         lower = -alpha if symmetric else torch.zeros(1)
         torch.clamp(xr, lower, alpha).backward(gy)
-        gx, g_hi, g_lo = oqdq.clamp_backward(x.numpy(), gy.numpy(), float(lower), 1.5)
+        gx, g_hi, g_lo = oqdq.clamp_backward(x.numpy(), gy.numpy(), float(lower.detach()), 1.5)
         assert np.array_equal(gx, xr.grad.numpy())
         expect = g_hi - g_lo if symmetric else g_hi
         np.testing.assert_allclose(float(alpha.grad), expect, rtol=1e-5)
